@@ -1,0 +1,183 @@
+/*
+ * rtoctree_b200.h — C ABI of librtoctree_b200.so, the B200-native (sm_100a) RT-Octree render hot path.
+ *
+ * The reference (LumiOwO/RT-Octree) has no FFI layer: its boundary is the C++ API of two static libraries
+ * (`volrend`, `volrend_denoiser`) plus the `volrend_headless` CLI and file formats.  This header
+ * is the thin C layer the north star asks for; every entry point names the reference interface it replaces.
+ * The C++ classes in rt_octree_b200/host/volrend_b200.hpp mirror the reference classes one-to-one on top of it,
+ * and rt_octree_b200/capi.py binds it with ctypes for the tests and bench.py.  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns RTO_OK (0) or a negative rto_status and
+ * leaves a message for rto_last_error() (thread-local).  `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream); all render/denoise calls are asynchronous on it, exactly like launch_renderer /
+ * Denoiser::denoise.  There is NO CPU fallback: without a usable CUDA device every call that needs one fails
+ * with RTO_ERR_CUDA.
+ */
+#ifndef RTOCTREE_B200_H_
+#define RTOCTREE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTO_ABI_VERSION 1
+
+typedef enum rto_status {
+    RTO_OK = 0,
+    RTO_ERR_INVALID = -1,      /* bad argument / malformed tree (the reference throws std::runtime_error) */
+    RTO_ERR_UNSUPPORTED = -2,  /* e.g. spp not in {1,2,3,4,6,8,16,32}: renderer/src/cuda/volrend.cu:266-278 */
+    RTO_ERR_CUDA = -3,         /* CUDA runtime error (the reference prints, cudaDeviceReset()s and exits:
+                                  renderer/src/cuda/common.cu:8-21; a library must not exit) */
+    RTO_ERR_NOMEM = -4
+} rto_status;
+
+/* DataFormat::format, renderer/include/volrend/data_format.hpp:9-16 */
+typedef enum rto_data_format { RTO_FORMAT_RGBA = 0, RTO_FORMAT_SH = 1, RTO_FORMAT_SG = 2, RTO_FORMAT_ASG = 3 } rto_data_format;
+
+typedef struct rto_tree rto_tree;       /* replaces volrend::N3Tree (device side)   include/volrend/n3tree.hpp:24-106 */
+typedef struct rto_context rto_context; /* replaces volrend::RenderContext          include/volrend/render_context.hpp:14-120 */
+typedef struct rto_net rto_net;         /* replaces volrend::Denoiser               include/volrend/denoiser/denoiser.hpp:11-21 */
+
+/* Camera + CameraSpec (include/volrend/camera.hpp:16-68, internal/data_spec.hpp:11-26).  c2w is the column-major
+ * 4x3 camera-to-world transform Camera::_update uploads (src/camera.cpp:72-73): right, up, back, centre. */
+typedef struct rto_camera {
+    int width, height;
+    float fx, fy;
+    float c2w[12];
+} rto_camera;
+
+/* RenderOptions (include/volrend/render_options.hpp:13-78).  The JSON binding carries 11 keys (:61-77); keys that
+ * only drive the GUI (show_grid, grid_max_depth, probe*) are parsed by the host layer and are not needed here.
+ * enable_probe must be 0 (lumisphere probe is out of scope). */
+typedef struct rto_render_options {
+    float step_size;              /* 1e-4 */
+    float sigma_thresh;           /* 1e-2 */
+    float stop_thresh;            /* parsed, unused by the CUDA path (only shaders/rt.frag:314) */
+    float background_brightness;  /* 1.0 */
+    int denoise;                  /* 1: final image is produced by rto_denoise, rto_render writes only aux */
+    int spp;                      /* 1,2,3,4,6,8,16,32 */
+    int enable_probe;             /* must be 0 */
+} rto_render_options;
+void rto_render_options_default(rto_render_options* opt); /* reference defaults, spp = 1, denoise = 1 */
+
+typedef struct rto_tree_info {
+    int64_t capacity;        /* nodes */
+    int N, data_dim, format, basis_dim;
+    int max_depth;           /* max child look-ups to reach a leaf */
+    int64_t n_leaves;
+    int64_t node_bytes, payload_bytes; /* HBM footprint of the SoA layout */
+    int payload_stride_halfs;
+    float offset[3], scale[3];
+    float ndc_width, ndc_height, ndc_focal;
+} rto_tree_info;
+
+/* Per-ray traversal record for the bit-exact parity tests (all DEVICE pointers, any may be NULL), indexed by
+ * the full-frame pixel index iy*W+ix.  Definitions in oracle/rt_oracle.c (trace_t). */
+typedef struct rto_trace {
+    uint32_t* steps;      /* leaf visits */
+    int32_t* term;        /* step index of the SPP-th collision, or -1 */
+    uint32_t* src_bits;   /* fp32 bits of the accumulated optical depth at exit */
+    uint32_t* t_bits;     /* fp32 bits of t at exit */
+    uint64_t* leaf_hash;  /* FNV-1a 64 over visited leaf indices */
+    uint32_t* depth_sum;  /* sum of child look-ups the REFERENCE's root-restart query would do (sum of leaf depths) */
+    uint32_t* n_hits;     /* collided-leaf entries (sh_nums) */
+    uint32_t* n_loads;    /* node words this implementation actually loaded (ancestor-resume descent) */
+    int32_t* hit_leaf;    /* [n][spp] */
+    uint32_t* hit_cnt;    /* [n][spp] */
+    int32_t* leaf_seq;    /* [n][max_seq] */
+    float* thresh;        /* [n][spp] sorted thresholds dst[] (lg2.approx based) */
+    int max_seq;
+} rto_trace;
+
+const char* rto_last_error(void);
+int rto_abi_version(void);
+/* cudaSetDevice — main_headless.cpp:234-238 (`--gpu`).  */
+int rto_set_device(int device);
+int rto_device_count(int* count);
+/* cudaStreamSynchronize(stream) (stream == NULL: cudaDeviceSynchronize) — what Timer::record / cudaMemcpy do implicitly */
+int rto_synchronize(void* stream);
+
+/* ---- tree : N3Tree::load_npz result -> N3Tree::load_cuda (src/n3tree.cpp:228-362, src/cuda/n3tree.cu:9-41) ----
+ * Host arrays exactly as they sit in tree.npz: child int32 [capacity][N][N][N] (relative node offsets, 0 = leaf),
+ * data fp16 [capacity][N][N][N][data_dim] (last = sigma).  The call uploads them and re-lays them out ON THE GPU
+ * as structure-of-arrays (node words with embedded sigma + padded fp16 payload plane).  N must be 2. */
+int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, int64_t capacity, int N,
+                    int data_dim, int format, int basis_dim, const float offset[3], const float scale[3]);
+/* main_headless.cpp:400-405 / n3tree.hpp:69-71: NDC warp for forward-facing (llff) scenes; width<=0 disables. */
+int rto_tree_set_ndc(rto_tree* tree, float ndc_width, float ndc_height, float ndc_focal);
+int rto_tree_get_info(const rto_tree* tree, rto_tree_info* info);
+void rto_tree_destroy(rto_tree* tree); /* N3Tree::~N3Tree -> free_cuda */
+
+/* ---- context : RenderContext::update / freeResource (render_context.hpp:42-120) ----
+ * Owns aux [8][H][W] fp32, the output image [H][W][4] fp32 (linear memory instead of a cudaArray surface), the
+ * GuidanceNet scratch maps, the pcg32 state (seed 20230418, :16) and the three-stage event timer (:122-213). */
+int rto_context_create(rto_context** out, int width, int height);
+void rto_context_destroy(rto_context* ctx);
+float* rto_context_aux(rto_context* ctx);    /* device pointer, RenderContext::aux_buffer */
+float* rto_context_image(rto_context* ctx);  /* device pointer, float4 per pixel */
+/* ctx.rng: pcg32(seed) ; advance(delta) with the reference default delta = 2^32 (pcg32.h:145) */
+int rto_context_rng_seed(rto_context* ctx, uint64_t seed);
+int rto_context_rng_advance(rto_context* ctx, int64_t delta);
+/* Pure function of the frame index: state = pcg32(20230418) advanced by (warmup + frame) * 2^32, which is what
+ * main_headless.cpp:469-479,506 leaves in ctx.rng when it renders pose `frame` (warmup = 100 there).  Lets any
+ * rank of a frame-sharded job reproduce the single-GPU image bit for bit. */
+int rto_context_rng_set_frame(rto_context* ctx, int64_t warmup, int64_t frame);
+int rto_context_rng_get(const rto_context* ctx, uint64_t* state, uint64_t* inc);
+/* cudaMemcpy(…, DeviceToHost) of aux (main_headless.cpp:516-517) / image (:526-534); async on `stream`. */
+int rto_context_read_aux(rto_context* ctx, float* host_dst, void* stream);
+int rto_context_read_image(rto_context* ctx, float* host_dst, void* stream);
+
+/* ---- render : volrend::launch_renderer(tree, cam, options, ctx, stream, offscreen=true)
+ *               include/volrend/cuda/renderer_kernel.hpp:11-16, src/cuda/volrend.cu:236-285 ---- */
+int rto_render(rto_context* ctx, const rto_tree* tree, const rto_camera* cam, const rto_render_options* opt,
+               void* stream);
+/* Same, restricted to the pixel rectangle [x0,x1) x [y0,y1) (single-frame tile split); pixel
+ * indices, RNG offsets and buffer addresses stay full-frame. */
+int rto_render_rect(rto_context* ctx, const rto_tree* tree, const rto_camera* cam, const rto_render_options* opt,
+                    int x0, int y0, int x1, int y1, void* stream);
+/* Same kernel with the per-ray traversal record switched on (parity tests only). */
+int rto_render_trace(rto_context* ctx, const rto_tree* tree, const rto_camera* cam, const rto_render_options* opt,
+                     const rto_trace* trace, void* stream);
+
+/* ---- denoiser : Denoiser(ts_module_path) / Denoiser::denoise(cam, ctx, stream)  (src/denoiser/denoiser.cpp:8-71)
+ * Weights are the four fp16 tensors of the deployed GuidanceNet (network.py:123-168), exported once from the
+ * reference's ts_*.ts by tools/export_guidance_net.py: w1 [mid][in][3][3], b1 [mid], w2 [2L][mid][3][3], b2 [2L]. */
+int rto_net_create(rto_net** out, const void* w1_f16, const void* b1_f16, const void* w2_f16, const void* b2_f16,
+                   int in_ch, int mid_ch, int levels);
+void rto_net_destroy(rto_net* net);
+/* implementation selector: 0 = auto (tensor-core kernel when the net is the shipped 8->32->8, L=4 shape),
+ * 1 = force the generic CUDA-core kernels (bring-up / cross-check path) */
+int rto_net_set_impl(rto_net* net, int impl);
+/* fp16 rounding of the conv bias add: 0 (default) = half(half(acc)+b), ATen's cuDNN path (cudnn_convolution, then
+ * output.add_(bias)) that the reference runs on the GPU; 1 = half(acc+b), what PyTorch's CPU fp16 conv computes. */
+int rto_net_set_bias_mode(rto_net* net, int fused);
+int rto_denoise(rto_context* ctx, const rto_net* net, void* stream);
+int rto_denoise_rows(rto_context* ctx, const rto_net* net, int y0, int y1, void* stream);
+/* The two halves on their own, on caller-provided DEVICE buffers:
+ * ts_module.forward(aux) -> (weight_map [L][H][W], guidance_map [L][H][W])           denoiser.cpp:46-48 */
+int rto_net_forward(const rto_net* net, const float* aux_dev, int width, int height, float* weight_dev,
+                    float* guidance_dev, void* stream);
+/* denoiser::filtering(stream, weight_map, guidance_map, img_in, img_out)  denoiser/extension/filtering.h:7-13
+ * img_in / img_out: [H][W][4] fp32 device buffers; L in 1..6 (filtering.cu:338-367). */
+int rto_filter(const float* weight_dev, const float* guidance_dev, const float* img_in_dev, int levels, int width,
+               int height, float* img_out_dev, void* stream);
+
+/* ---- timer : RenderContext::Timer (render_context.hpp:122-213) ----
+ * With timing enabled rto_render / rto_denoise bracket their launches with cudaEvents on `stream`;
+ * rto_timer_record synchronises on the last stop event and accumulates (Timer::record).  ms[0..2] = mean
+ * render / net / filter ms per recorded frame (Timer::report); FPS = 1000 / (ms[0]+ms[1]+ms[2]). */
+int rto_timer_enable(rto_context* ctx, int enable);
+int rto_timer_reset(rto_context* ctx);
+int rto_timer_record(rto_context* ctx, int denoise);
+int rto_timer_report(const rto_context* ctx, float ms[3], int* frames);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches evidence) */
+int64_t rto_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTOCTREE_B200_H_ */

@@ -1,0 +1,499 @@
+// rto_api.cu — the extern "C" layer declared in include/rtoctree_b200.h.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/rtoctree_b200.h"
+#include "rto_internal.h"
+
+namespace rto {
+cudaError_t launch_build_nodes(const int32_t*, const __half*, int, int64_t, int64_t, uint32_t*, unsigned long long*,
+                               int*, cudaStream_t);
+cudaError_t launch_build_payload(const __half*, int, int, int64_t, __half*, cudaStream_t);
+int tree_max_depth_host(const int32_t* child, int64_t capacity);
+cudaError_t launch_denoise_tc(const NetDev& net, const void* packed_weights, const DenoiseArgs& d, cudaStream_t stream);
+size_t denoise_tc_packed_bytes();
+cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream);
+}  // namespace rto
+
+struct rto_tree {
+    uint32_t* nodes = nullptr;
+    __half* payload = nullptr;
+    rto_tree_info info{};
+};
+
+struct rto_context {
+    int W = 0, H = 0;
+    float* aux = nullptr;
+    float4* img = nullptr;
+    float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
+    float* guidance_map = nullptr;
+    rto::Pcg32 rng{};
+    // Timer
+    bool timing = false;
+    cudaEvent_t ev_start[3]{}, ev_stop[3]{};
+    bool ev_used[3]{};
+    cudaStream_t timer_stream = nullptr;
+    float sum_ms[3]{};
+    int frames = 0;
+};
+
+struct rto_net {
+    __half *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    void* packed = nullptr;   // tensor-core operand images (rto_denoise_tc.cu)
+    int in_ch = 0, mid_ch = 0, levels = 0;
+    int impl = 0;
+    int fused_bias = 0;
+    rto::NetDev dev() const { return rto::NetDev{w1, b1, w2, b2, in_ch, mid_ch, levels, fused_bias}; }
+    bool tc_capable() const { return in_ch == 8 && mid_ch == 32 && levels == 4 && packed != nullptr; }
+};
+
+namespace {
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define RTO_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(RTO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+void pcg32_seed(rto::Pcg32& r, uint64_t initstate, uint64_t initseq = 1) {  // pcg32.h:53-59
+    r.state = 0u;
+    r.inc = (initseq << 1u) | 1u;
+    rto::pcg32_next(r);
+    r.state += initstate;
+    rto::pcg32_next(r);
+}
+
+int check_opt(const rto_render_options* opt) {
+    if (!opt) return fail(RTO_ERR_INVALID, "options is NULL");
+    if (opt->enable_probe) return fail(RTO_ERR_UNSUPPORTED, "enable_probe is not supported (lumisphere probe is out of scope)");
+    switch (opt->spp) {
+        case 1: case 2: case 3: case 4: case 6: case 8: case 16: case 32: return RTO_OK;
+        default: return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp);  // volrend.cu:275-277
+    }
+}
+
+void timer_start(rto_context* c, int i, cudaStream_t s) {
+    if (!c->timing) return;
+    c->timer_stream = s;
+    cudaEventRecord(c->ev_start[i], s);
+}
+void timer_stop(rto_context* c, int i, cudaStream_t s) {
+    if (!c->timing) return;
+    cudaEventRecord(c->ev_stop[i], s);
+    c->ev_used[i] = true;
+}
+}  // namespace
+
+extern "C" {
+
+const char* rto_last_error(void) { return g_err.c_str(); }
+int rto_abi_version(void) { return RTO_ABI_VERSION; }
+int64_t rto_launch_count(void) { return g_launches.load(); }
+
+int rto_set_device(int device) {
+    RTO_CUDA(cudaSetDevice(device));
+    return RTO_OK;
+}
+int rto_device_count(int* count) {
+    if (!count) return fail(RTO_ERR_INVALID, "count is NULL");
+    RTO_CUDA(cudaGetDeviceCount(count));
+    return RTO_OK;
+}
+
+int rto_synchronize(void* stream) {
+    if (stream) RTO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    else RTO_CUDA(cudaDeviceSynchronize());
+    return RTO_OK;
+}
+
+void rto_render_options_default(rto_render_options* o) {
+    if (!o) return;
+    o->step_size = 1e-4f;
+    o->sigma_thresh = 1e-2f;
+    o->stop_thresh = 1e-2f;
+    o->background_brightness = 1.f;
+    o->denoise = 1;
+    o->spp = 1;
+    o->enable_probe = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- tree
+int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, int64_t capacity, int N,
+                    int data_dim, int format, int basis_dim, const float offset[3], const float scale[3]) {
+    if (!out || !child || !data_f16 || !offset || !scale) return fail(RTO_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (N != 2) return fail(RTO_ERR_UNSUPPORTED, "N == %d: only N = 2 octrees are supported (n3tree.cpp:273-275 warns the same)", N);
+    if (capacity <= 0 || capacity >= (int64_t)1 << 28) return fail(RTO_ERR_INVALID, "capacity %lld out of range", (long long)capacity);
+    if (format == RTO_FORMAT_SG || format == RTO_FORMAT_ASG)
+        return fail(RTO_ERR_UNSUPPORTED, "SG/ASG data formats are not supported (SH and RGBA only)");
+    if (format == RTO_FORMAT_SH) {
+        if (!(basis_dim == 1 || basis_dim == 4 || basis_dim == 9 || basis_dim == 16 || basis_dim == 25))
+            return fail(RTO_ERR_INVALID, "SH basis_dim %d not in {1,4,9,16,25}", basis_dim);
+        if (data_dim != 3 * basis_dim + 1) return fail(RTO_ERR_INVALID, "data_dim %d != 3*%d+1", data_dim, basis_dim);
+    } else if (format == RTO_FORMAT_RGBA) {
+        if (data_dim != 4) return fail(RTO_ERR_INVALID, "RGBA format needs data_dim 4, got %d", data_dim);
+        basis_dim = -1;
+    } else {
+        return fail(RTO_ERR_INVALID, "unknown data format %d", format);
+    }
+    const int max_depth = rto::tree_max_depth_host(child, capacity);
+    if (max_depth < 0) return fail(RTO_ERR_INVALID, "malformed tree: child offset leaves the node array or the links form a cycle");
+    if (max_depth > RTO_COORD_BITS) return fail(RTO_ERR_UNSUPPORTED, "tree depth %d exceeds %d levels", max_depth, RTO_COORD_BITS);
+
+    rto_tree* t = new (std::nothrow) rto_tree;
+    if (!t) return fail(RTO_ERR_NOMEM, "out of host memory");
+    const int64_t n_entries = capacity * 8;
+    const int stride = ((data_dim - 1) + 7) / 8 * 8;
+    int32_t* d_child = nullptr;
+    __half* d_data = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    int* d_bad = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_child); cudaFree(d_data); cudaFree(d_cnt); cudaFree(d_bad);
+    };
+    auto bail = [&](cudaError_t e, const char* what) {
+        cleanup();
+        cudaFree(t->nodes); cudaFree(t->payload);
+        delete t;
+        return fail(e == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_child, n_entries * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc(child)");
+    if ((e = cudaMalloc(&d_data, (size_t)n_entries * data_dim * sizeof(__half))) != cudaSuccess) return bail(e, "cudaMalloc(data)");
+    if ((e = cudaMalloc(&t->nodes, n_entries * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc(nodes)");
+    if ((e = cudaMalloc(&t->payload, (size_t)n_entries * stride * sizeof(__half))) != cudaSuccess) return bail(e, "cudaMalloc(payload)");
+    if ((e = cudaMalloc(&d_cnt, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(d_cnt, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMemset(d_bad, 0, sizeof(int))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMemcpy(d_child, child, n_entries * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D child");
+    if ((e = cudaMemcpy(d_data, data_f16, (size_t)n_entries * data_dim * sizeof(__half), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D data");
+    if ((e = rto::launch_build_nodes(d_child, d_data, data_dim, n_entries, capacity, t->nodes, d_cnt, d_bad, nullptr)) != cudaSuccess) return bail(e, "build_nodes");
+    if ((e = rto::launch_build_payload(d_data, data_dim, stride, n_entries, t->payload, nullptr)) != cudaSuccess) return bail(e, "build_payload");
+    g_launches += 2;
+    unsigned long long n_leaves = 0;
+    int bad = 0;
+    if ((e = cudaMemcpy(&n_leaves, d_cnt, sizeof n_leaves, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail(e, "D2H");
+    if ((e = cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail(e, "D2H");
+    cleanup();
+    if (bad) {
+        cudaFree(t->nodes); cudaFree(t->payload);
+        delete t;
+        return fail(RTO_ERR_INVALID, "malformed tree: child offset out of range");
+    }
+    rto_tree_info& I = t->info;
+    I.capacity = capacity; I.N = N; I.data_dim = data_dim; I.format = format; I.basis_dim = basis_dim;
+    I.max_depth = max_depth; I.n_leaves = (int64_t)n_leaves;
+    I.node_bytes = n_entries * (int64_t)sizeof(uint32_t);
+    I.payload_bytes = n_entries * (int64_t)stride * (int64_t)sizeof(__half);
+    I.payload_stride_halfs = stride;
+    for (int i = 0; i < 3; ++i) { I.offset[i] = offset[i]; I.scale[i] = scale[i]; }
+    I.ndc_width = -1.f; I.ndc_height = 0.f; I.ndc_focal = 0.f;
+    *out = t;
+    return RTO_OK;
+}
+
+int rto_tree_set_ndc(rto_tree* t, float w, float h, float f) {
+    if (!t) return fail(RTO_ERR_INVALID, "tree is NULL");
+    t->info.ndc_width = w; t->info.ndc_height = h; t->info.ndc_focal = f;
+    return RTO_OK;
+}
+int rto_tree_get_info(const rto_tree* t, rto_tree_info* info) {
+    if (!t || !info) return fail(RTO_ERR_INVALID, "NULL argument");
+    *info = t->info;
+    return RTO_OK;
+}
+void rto_tree_destroy(rto_tree* t) {
+    if (!t) return;
+    cudaFree(t->nodes);
+    cudaFree(t->payload);
+    delete t;
+}
+
+// ------------------------------------------------------------------------------------------------- context
+int rto_context_create(rto_context** out, int W, int H) {
+    if (!out) return fail(RTO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (W <= 0 || H <= 0 || (int64_t)W * H > (int64_t)1 << 28) return fail(RTO_ERR_INVALID, "bad image size %dx%d", W, H);
+    rto_context* c = new (std::nothrow) rto_context;
+    if (!c) return fail(RTO_ERR_NOMEM, "out of host memory");
+    c->W = W; c->H = H;
+    const size_t px = (size_t)W * H;
+    cudaError_t e = cudaMalloc(&c->aux, px * 8 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->img, px * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&c->weight_map, px * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->guidance_map, px * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->aux, 0, px * 8 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->img, 0, px * sizeof(float4));
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+        e = cudaEventCreate(&c->ev_start[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&c->ev_stop[i]);
+    }
+    if (e != cudaSuccess) {
+        rto_context_destroy(c);
+        return fail(e == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "context allocation: %s", cudaGetErrorString(e));
+    }
+    pcg32_seed(c->rng, 20230418ull);  // render_context.hpp:16
+    *out = c;
+    return RTO_OK;
+}
+void rto_context_destroy(rto_context* c) {
+    if (!c) return;
+    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map);
+    for (int i = 0; i < 3; ++i) {
+        if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
+        if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
+    }
+    delete c;
+}
+float* rto_context_aux(rto_context* c) { return c ? c->aux : nullptr; }
+float* rto_context_image(rto_context* c) { return c ? reinterpret_cast<float*>(c->img) : nullptr; }
+int rto_context_rng_seed(rto_context* c, uint64_t seed) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    pcg32_seed(c->rng, seed);
+    return RTO_OK;
+}
+int rto_context_rng_advance(rto_context* c, int64_t delta) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    rto::pcg32_advance(c->rng, (uint64_t)delta);
+    return RTO_OK;
+}
+int rto_context_rng_set_frame(rto_context* c, int64_t warmup, int64_t frame) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    pcg32_seed(c->rng, 20230418ull);
+    // (warmup+frame) calls of advance(2^32) compose to one advance((warmup+frame)*2^32) (mod 2^64)
+    rto::pcg32_advance(c->rng, (uint64_t)(warmup + frame) << 32);
+    return RTO_OK;
+}
+int rto_context_rng_get(const rto_context* c, uint64_t* state, uint64_t* inc) {
+    if (!c || !state || !inc) return fail(RTO_ERR_INVALID, "NULL argument");
+    *state = c->rng.state; *inc = c->rng.inc;
+    return RTO_OK;
+}
+int rto_context_read_aux(rto_context* c, float* dst, void* stream) {
+    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    RTO_CUDA(cudaMemcpyAsync(dst, c->aux, (size_t)c->W * c->H * 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RTO_OK;
+}
+int rto_context_read_image(rto_context* c, float* dst, void* stream) {
+    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    RTO_CUDA(cudaMemcpyAsync(dst, c->img, (size_t)c->W * c->H * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RTO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- render
+static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt,
+                       int x0, int y0, int x1, int y1, const rto_trace* trace, void* stream) {
+    if (!c || !t || !cam) return fail(RTO_ERR_INVALID, "NULL argument");
+    int rc = check_opt(opt);
+    if (rc != RTO_OK) return rc;
+    if (cam->width != c->W || cam->height != c->H)
+        return fail(RTO_ERR_INVALID, "camera %dx%d does not match context %dx%d", cam->width, cam->height, c->W, c->H);
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 > c->W ? c->W : x1; y1 = y1 > c->H ? c->H : y1;
+    rto::RenderArgs a{};
+    rto::FrameParams& fp = a.fp;
+    memcpy(fp.c2w, cam->c2w, sizeof fp.c2w);
+    for (int i = 0; i < 3; ++i) { fp.offset[i] = t->info.offset[i]; fp.scale[i] = t->info.scale[i]; }
+    fp.fx = cam->fx; fp.fy = cam->fy;
+    fp.ndc_width = t->info.ndc_width; fp.ndc_height = t->info.ndc_height; fp.ndc_focal = t->info.ndc_focal;
+    fp.step_size = opt->step_size; fp.sigma_thresh = opt->sigma_thresh; fp.background = opt->background_brightness;
+    fp.W = c->W; fp.H = c->H;
+    a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth};
+    a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
+    a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
+    a.aux = c->aux;
+    // with the denoiser on, the final image comes from rto_denoise; the reference then renders into a separate
+    // noisy surface whose rgb equals aux channels 0..2 (volrend.cu:188-192 vs :205-212), so nothing is lost here
+    a.img = opt->denoise ? nullptr : c->img;
+    if (trace) {
+        a.tr = rto::TraceOut{trace->steps, trace->term, trace->src_bits, trace->t_bits, trace->leaf_hash,
+                             trace->depth_sum, trace->n_hits, trace->n_loads, trace->hit_leaf, trace->hit_cnt,
+                             trace->leaf_seq, trace->thresh, trace->max_seq};
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    timer_start(c, 0, s);
+    bool bad_spp = false;
+    cudaError_t e = rto::launch_render(a, opt->spp, trace != nullptr, s, &bad_spp);
+    timer_stop(c, 0, s);
+    if (bad_spp) return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return RTO_OK;
+}
+int rto_render(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt, void* stream) {
+    return render_impl(c, t, cam, opt, 0, 0, c ? c->W : 0, c ? c->H : 0, nullptr, stream);
+}
+int rto_render_rect(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt, int x0,
+                    int y0, int x1, int y1, void* stream) {
+    return render_impl(c, t, cam, opt, x0, y0, x1, y1, nullptr, stream);
+}
+int rto_render_trace(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt,
+                     const rto_trace* trace, void* stream) {
+    if (!trace) return fail(RTO_ERR_INVALID, "trace is NULL");
+    return render_impl(c, t, cam, opt, 0, 0, c ? c->W : 0, c ? c->H : 0, trace, stream);
+}
+
+// ------------------------------------------------------------------------------------------------- denoiser
+int rto_net_create(rto_net** out, const void* w1, const void* b1, const void* w2, const void* b2, int in_ch,
+                   int mid_ch, int levels) {
+    if (!out || !w1 || !b1 || !w2 || !b2) return fail(RTO_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (in_ch != 8) return fail(RTO_ERR_UNSUPPORTED, "in_channels %d: the aux buffer has 8 channels (RenderContext::CHANNELS)", in_ch);
+    if (mid_ch < 1 || mid_ch > 64) return fail(RTO_ERR_UNSUPPORTED, "mid_channels %d not in 1..64", mid_ch);
+    if (levels < 1 || levels > 6) return fail(RTO_ERR_UNSUPPORTED, "Kernel size == %d not supported.", levels * 2 + 1);  // filtering.cu:362-366
+    rto_net* n = new (std::nothrow) rto_net;
+    if (!n) return fail(RTO_ERR_NOMEM, "out of host memory");
+    n->in_ch = in_ch; n->mid_ch = mid_ch; n->levels = levels;
+    const size_t n1 = (size_t)mid_ch * in_ch * 9, n2 = (size_t)2 * levels * mid_ch * 9;
+    cudaError_t e = cudaMalloc(&n->w1, n1 * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&n->b1, (size_t)mid_ch * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&n->w2, n2 * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&n->b2, (size_t)2 * levels * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(n->w1, w1, n1 * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(n->b1, b1, (size_t)mid_ch * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(n->w2, w2, n2 * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(n->b2, b2, (size_t)2 * levels * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && in_ch == 8 && mid_ch == 32 && levels == 4 && rto::denoise_tc_packed_bytes() > 0) {
+        e = cudaMalloc(&n->packed, rto::denoise_tc_packed_bytes());
+        if (e == cudaSuccess) e = rto::denoise_tc_pack_weights(n->dev(), n->packed, nullptr);
+        if (e == cudaSuccess) { ++g_launches; e = cudaDeviceSynchronize(); }
+    }
+    if (e != cudaSuccess) {
+        rto_net_destroy(n);
+        return fail(e == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "net upload: %s", cudaGetErrorString(e));
+    }
+    *out = n;
+    return RTO_OK;
+}
+void rto_net_destroy(rto_net* n) {
+    if (!n) return;
+    cudaFree(n->w1); cudaFree(n->b1); cudaFree(n->w2); cudaFree(n->b2); cudaFree(n->packed);
+    delete n;
+}
+int rto_net_set_impl(rto_net* n, int impl) {
+    if (!n) return fail(RTO_ERR_INVALID, "net is NULL");
+    if (impl != 0 && impl != 1) return fail(RTO_ERR_INVALID, "impl must be 0 (auto) or 1 (simt)");
+    n->impl = impl;
+    return RTO_OK;
+}
+
+int rto_net_set_bias_mode(rto_net* n, int fused) {
+    if (!n) return fail(RTO_ERR_INVALID, "net is NULL");
+    n->fused_bias = fused != 0;
+    return RTO_OK;
+}
+
+int rto_denoise_rows(rto_context* c, const rto_net* n, int y0, int y1, void* stream) {
+    if (!c || !n) return fail(RTO_ERR_INVALID, "NULL argument");
+    y0 = y0 < 0 ? 0 : y0; y1 = y1 > c->H ? c->H : y1;
+    cudaStream_t s = (cudaStream_t)stream;
+    rto::DenoiseArgs d{c->aux, c->img, c->weight_map, c->guidance_map, c->W, c->H, y0, y1};
+    if (n->impl == 0 && n->tc_capable()) {
+        timer_start(c, 1, s);
+        cudaError_t e = rto::launch_denoise_tc(n->dev(), n->packed, d, s);
+        timer_stop(c, 1, s);
+        if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "denoise (tensor-core) launch: %s", cudaGetErrorString(e));
+        ++g_launches;
+        // single fused kernel: the "filter" stage has no launch of its own; its events bracket nothing
+        timer_start(c, 2, s);
+        timer_stop(c, 2, s);
+        return RTO_OK;
+    }
+    // net rows must cover the filter's halo: the filter at row y reads guidance rows y-L..y+L
+    const int L = n->levels;
+    rto::DenoiseArgs dn = d;
+    dn.y0 = y0 - L < 0 ? 0 : y0 - L;
+    dn.y1 = y1 + L > c->H ? c->H : y1 + L;
+    timer_start(c, 1, s);
+    cudaError_t e = rto::launch_guidance_net_simt(n->dev(), dn, s);
+    timer_stop(c, 1, s);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch: %s", cudaGetErrorString(e));
+    timer_start(c, 2, s);
+    e = rto::launch_filter_simt(c->aux, (size_t)c->W * c->H, 1, c->weight_map, c->guidance_map, L, c->W, c->H, y0, y1,
+                                c->img, s);
+    timer_stop(c, 2, s);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    return RTO_OK;
+}
+int rto_denoise(rto_context* c, const rto_net* n, void* stream) {
+    return rto_denoise_rows(c, n, 0, c ? c->H : 0, stream);
+}
+
+int rto_net_forward(const rto_net* n, const float* aux_dev, int W, int H, float* weight_dev, float* guidance_dev,
+                    void* stream) {
+    if (!n || !aux_dev || !weight_dev || !guidance_dev) return fail(RTO_ERR_INVALID, "NULL argument");
+    if (W <= 0 || H <= 0) return fail(RTO_ERR_INVALID, "bad size");
+    rto::DenoiseArgs d{aux_dev, nullptr, weight_dev, guidance_dev, W, H, 0, H};
+    cudaError_t e = rto::launch_guidance_net_simt(n->dev(), d, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return RTO_OK;
+}
+
+int rto_filter(const float* weight_dev, const float* guidance_dev, const float* img_in_dev, int L, int W, int H,
+               float* img_out_dev, void* stream) {
+    if (!weight_dev || !guidance_dev || !img_in_dev || !img_out_dev) return fail(RTO_ERR_INVALID, "NULL argument");
+    if (L < 1 || L > 6) return fail(RTO_ERR_UNSUPPORTED, "Kernel size == %d not supported.", L * 2 + 1);
+    if (W <= 0 || H <= 0) return fail(RTO_ERR_INVALID, "bad size");
+    cudaError_t e = rto::launch_filter_simt(img_in_dev, 1, 4, weight_dev, guidance_dev, L, W, H, 0, H,
+                                            reinterpret_cast<float4*>(img_out_dev), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return RTO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- timer
+int rto_timer_enable(rto_context* c, int enable) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    c->timing = enable != 0;
+    return RTO_OK;
+}
+int rto_timer_reset(rto_context* c) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    c->frames = 0;
+    for (int i = 0; i < 3; ++i) { c->sum_ms[i] = 0.f; c->ev_used[i] = false; }
+    return RTO_OK;
+}
+int rto_timer_record(rto_context* c, int denoise) {  // Timer::record, render_context.hpp:179-188
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    if (!c->timing) return fail(RTO_ERR_INVALID, "timer not enabled");
+    const int last = denoise ? 2 : 0;
+    if (!c->ev_used[last]) return fail(RTO_ERR_INVALID, "nothing recorded for this frame");
+    RTO_CUDA(cudaEventSynchronize(c->ev_stop[last]));
+    c->frames++;
+    for (int i = 0; i < 3; ++i) {
+        if (!c->ev_used[i] || (!denoise && i > 0)) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_start[i], c->ev_stop[i]) == cudaSuccess) c->sum_ms[i] += ms;
+    }
+    return RTO_OK;
+}
+int rto_timer_report(const rto_context* c, float ms[3], int* frames) {
+    if (!c || !ms) return fail(RTO_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 3; ++i) ms[i] = c->frames ? c->sum_ms[i] / c->frames : 0.f;
+    if (frames) *frames = c->frames;
+    return RTO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// rto_internal.h — device-side argument blocks shared by the kernels and the C-ABI layer (not installed).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "rto_ray.cuh"
+
+namespace rto {
+
+// HBM layout of a loaded tree (structure of arrays)
+struct TreeDev {
+    const uint32_t* nodes;  // [cap*8] node words: internal = ABSOLUTE child node id; leaf = 0x80000000 | sigma fp16 bits
+    const __half* sh;       // [cap*8][sh_stride] per-leaf colour payload (SH coefficients [3][basis] or rgb), fp16
+    int sh_stride;          // halfs per leaf, multiple of 8 (27 -> 32 = 64 B for SH9)
+    int basis_dim;          // >0: SH with that many coefficients per channel ; <=0: RGBA leaves
+    int max_depth;          // max child look-ups to reach a leaf (sizes the per-ray ancestor stack)
+};
+
+struct TraceOut {           // all optional (nullptr); indexed by the FULL-FRAME pixel index
+    uint32_t* steps;
+    int32_t* term;
+    uint32_t* src_bits;
+    uint32_t* t_bits;
+    uint64_t* leaf_hash;
+    uint32_t* depth_sum;
+    uint32_t* n_hits;
+    uint32_t* n_loads;
+    int32_t* hit_leaf;      // [n][spp]
+    uint32_t* hit_cnt;      // [n][spp]
+    int32_t* leaf_seq;      // [n][max_seq]
+    float* thresh;          // [n][spp] sorted thresholds dst[] as used by the kernel
+    int max_seq;
+};
+
+struct RenderArgs {
+    FrameParams fp;
+    TreeDev tree;
+    uint64_t rng_state, rng_inc;   // frame-level pcg32 state (ctx.rng passed by value: volrend.cu:90,157)
+    int x0, y0, x1, y1;            // pixel rectangle to render (full frame, or a band for the tile split)
+    float* aux;                    // [8][H][W] fp32
+    float4* img;                   // [H][W] float4, may be nullptr
+    TraceOut tr;
+};
+
+cudaError_t launch_render(const RenderArgs& a, int spp, bool trace, cudaStream_t stream, bool* bad_spp);
+
+// GuidanceNet (deployed form) weights on the device, fp16
+struct NetDev {
+    const __half* w1;  // [mid][in][3][3]
+    const __half* b1;  // [mid]
+    const __half* w2;  // [2L][mid][3][3]
+    const __half* b2;  // [2L]
+    int in_ch, mid_ch, levels;
+    int fused_bias;    // 0: half(half(acc)+b) (ATen cuDNN path, default) ; 1: half(acc+b) (PyTorch CPU fp16 conv)
+};
+
+struct DenoiseArgs {
+    const float* aux;      // [8][H][W]
+    float4* img_out;       // [H][W]
+    float* weight_map;     // [L][H][W] optional debug/inspection output (nullptr = not written)
+    float* guidance_map;   // [L][H][W] optional
+    int W, H;
+    int y0, y1;            // rows to produce (band for the tile split); input rows outside [0,H) are padding
+};
+
+}  // namespace rto
+
+namespace rto {
+cudaError_t launch_guidance_net_simt(const NetDev& net, const DenoiseArgs& d, cudaStream_t stream);
+// rgb[c*chan_stride + p*pix_stride]: (HW,1) for the planar aux buffer, (1,4) for an interleaved [H][W][4] image
+cudaError_t launch_filter_simt(const float* rgb, size_t chan_stride, int pix_stride, const float* weight,
+                               const float* guidance, int L, int W, int H, int y0, int y1, float4* out,
+                               cudaStream_t stream);
+}  // namespace rto

@@ -1,0 +1,199 @@
+// rto_render.cu — ray generation + regular-tracking octree traversal + SH shade/composite + aux/image writes.
+//
+// One launch replaces the reference's render_kernel<SPP> (renderer/src/cuda/volrend.cu:84-213) and everything it
+// inlines (rt_core.cuh:195-332, n3tree_query.hpp:13-48, lumisphere.hpp:38-81, pcg32.h).  Design:
+//   * a warp owns an 8x4 pixel tile (the reference maps 32 consecutive x to a warp) => coherent rays per warp,
+//     aux/image rows written as full 32 B sectors;
+//   * node words (child pointer | leaf flag + sigma) are 32 B per node, one sector;
+//   * per-ray ancestor stack in shared memory, integer-coordinate descent resumed at the common ancestor
+//     (rto_ray.cuh) instead of a root restart per step;
+//   * thresholds, hit list and counts live in registers for SPP <= 8 (the reference keeps them in local memory);
+//   * SH payload is a separate fp16 plane padded to 64 B per leaf and is touched only for collided leaves.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "rto_internal.h"
+#include "rto_ray.cuh"
+
+namespace rto {
+
+constexpr int kTileW = 8, kTileH = 4;      // pixels per warp
+constexpr int kWarpsX = 2, kWarpsY = 2;    // warps per block
+constexpr int kBlockThreads = 32 * kWarpsX * kWarpsY;
+
+struct SmemStack {
+    uint32_t* base;  // &stk[tid]
+    __device__ __forceinline__ uint32_t& operator()(int l) { return base[l * kBlockThreads]; }
+};
+
+template <int SPP, bool TRACE>
+__global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_constant__ RenderArgs a) {
+    extern __shared__ uint32_t stk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_x = blockIdx.x * (kTileW * kWarpsX) + (warp % kWarpsX) * kTileW;
+    const int tile_y = blockIdx.y * (kTileH * kWarpsY) + (warp / kWarpsX) * kTileH;
+    const int ix = a.x0 + tile_x + (lane & (kTileW - 1));
+    const int iy = a.y0 + tile_y + (lane / kTileW);
+    if (ix >= a.x1 || iy >= a.y1) return;
+    const FrameParams& fp = a.fp;
+    const int idx = iy * fp.W + ix;   // full-frame pixel index: RNG offset and aux address (volrend.cu:92-95)
+
+    RaySetup rs;
+    setup_ray(fp, ix, iy, rs);
+
+    float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
+    HitList<SPP> hits;
+    WalkOut wo;
+    {
+        float dst[SPP + 1];
+        if (rs.hit) sorted_thresholds<SPP>(a.rng_state, a.rng_inc, idx, dst);
+        if (TRACE && a.tr.thresh && rs.hit) {
+#pragma unroll
+            for (int i = 0; i < SPP; ++i) a.tr.thresh[(size_t)idx * SPP + i] = dst[i];
+        }
+        SmemStack stack{stk_smem + threadIdx.x};
+        auto sink = [&](uint32_t step, uint32_t leaf) {
+            if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
+        };
+        walk<SPP, TRACE>(a.tree.nodes, stack, rs, fp.step_size, fp.sigma_thresh, dst, hits, wo, sink);
+    }
+    const uint32_t sh_nums = hits.n;
+    const uint32_t (&hit_leaf)[SPP] = hits.leaf;
+    const float (&cnts)[SPP] = hits.cnt;
+
+    if (TRACE) {
+        const TraceOut& tr = a.tr;
+        if (tr.steps) tr.steps[idx] = wo.steps;
+        if (tr.term) tr.term[idx] = wo.term;
+        if (tr.src_bits) tr.src_bits[idx] = u_bits(wo.src);
+        if (tr.t_bits) tr.t_bits[idx] = u_bits(wo.t);
+        if (tr.leaf_hash) tr.leaf_hash[idx] = wo.hash;
+        if (tr.depth_sum) tr.depth_sum[idx] = wo.depth_sum;
+        if (tr.n_hits) tr.n_hits[idx] = sh_nums;
+        if (tr.n_loads) tr.n_loads[idx] = wo.n_loads;
+        for (int i = 0; i < SPP; ++i) {
+            if (tr.hit_leaf) tr.hit_leaf[(size_t)idx * SPP + i] = (int32_t)hit_leaf[i];
+            if (tr.hit_cnt) tr.hit_cnt[(size_t)idx * SPP + i] = (uint32_t)cnts[i];
+        }
+        if (tr.leaf_seq)
+            for (int s = (int)wo.steps; s < tr.max_seq; ++s) tr.leaf_seq[(size_t)idx * tr.max_seq + s] = -1;
+    }
+
+    if (sh_nums > 0) {
+        // accumulate colour (rt_core.cuh:277-331)
+        const int bd = a.tree.basis_dim;
+        const __half* __restrict__ sh = a.tree.sh;
+        const int stride = a.tree.sh_stride;
+        if (bd == 9) {
+            float b[9];
+            sh_basis(9, rs.vdir, b);
+#pragma unroll
+            for (int i = 0; i < SPP; ++i) {
+                if (i < (int)sh_nums) {
+                    const uint4* q = reinterpret_cast<const uint4*>(sh + (size_t)hit_leaf[i] * stride);
+                    uint32_t w[16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 v = __ldg(q + k);
+                        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                    }
+#define HV(k) f_half_bits_to_float((w[(k) >> 1] >> (((k) & 1) * 16)) & 0xffffu)
+                    float rgb[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+#define MB(k) (b[k] * HV(9 * c + (k)))
+                        float tmp = b[0] * HV(9 * c);
+                        tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
+                        tmp += MB(1) + MB(2) + MB(3);
+#undef MB
+                        rgb[c] = f_div(cnts[i], 1.f + f_exp(-tmp));
+                    }
+#undef HV
+                    out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
+                    out3 += cnts[i];
+                }
+            }
+        } else if (bd > 0) {
+            float b[25];
+#pragma unroll
+            for (int k = 0; k < 25; ++k) b[k] = 0.f;
+            sh_basis(bd, rs.vdir, b);
+            for (int i = 0; i < (int)sh_nums; ++i) {
+                const uint32_t leaf = selu(hit_leaf, i);
+                const float c_i = sel(cnts, i);
+                const __half* h = sh + (size_t)leaf * stride;
+                float rgb[3];
+                for (int c = 0; c < 3; ++c) {
+                    const __half* hc = h + bd * c;
+#define MB(k) (b[k] * __half2float(__ldg(hc + (k))))
+                    float tmp = b[0] * __half2float(__ldg(hc));
+                    if (bd >= 25) tmp += MB(16) + MB(17) + MB(18) + MB(19) + MB(20) + MB(21) + MB(22) + MB(23) + MB(24);
+                    if (bd >= 16) tmp += MB(9) + MB(10) + MB(11) + MB(12) + MB(13) + MB(14) + MB(15);
+                    if (bd >= 9) tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
+                    if (bd >= 4) tmp += MB(1) + MB(2) + MB(3);
+#undef MB
+                    rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
+                }
+                out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
+                out3 += c_i;
+            }
+        } else {  // RGBA leaves (rt_core.cuh:322-326)
+            for (int i = 0; i < (int)sh_nums; ++i) {
+                const uint32_t leaf = selu(hit_leaf, i);
+                const float c_i = sel(cnts, i);
+                const __half* h = sh + (size_t)leaf * stride;
+                out0 += __half2float(__ldg(h + 0)) * c_i;
+                out1 += __half2float(__ldg(h + 1)) * c_i;
+                out2 += __half2float(__ldg(h + 2)) * c_i;
+                out3 += c_i;
+            }
+        }
+        constexpr float INV_SPP = 1.0f / SPP;
+        out0 = f_mul(out0, INV_SPP); out1 = f_mul(out1, INV_SPP); out2 = f_mul(out2, INV_SPP); out3 = f_mul(out3, INV_SPP);
+    }
+
+    // background composite, offscreen branch (volrend.cu:174-179)
+    const float remain = f_mul(f_sub(1.f, out3), fp.background);
+    out0 = f_add(out0, remain); out1 = f_add(out1, remain); out2 = f_add(out2, remain);
+
+    // aux [8][H][W] (volrend.cu:187-202) and image [H][W][4] (volrend.cu:205-212)
+    if (a.aux) {
+        const size_t SIZE = (size_t)fp.W * fp.H;
+        float* q = a.aux + idx;
+        q[0] = out0; q[SIZE] = out1; q[2 * SIZE] = out2; q[3 * SIZE] = out3;
+        q[4 * SIZE] = f_mul(out0, out0); q[5 * SIZE] = f_mul(out1, out1);
+        q[6 * SIZE] = f_mul(out2, out2); q[7 * SIZE] = f_mul(out3, out3);
+    }
+    if (a.img) a.img[idx] = make_float4(out0, out1, out2, 1.0f);
+}
+
+template <int SPP>
+static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stream) {
+    const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
+    if (rw <= 0 || rh <= 0) return cudaSuccess;
+    dim3 grid((rw + kTileW * kWarpsX - 1) / (kTileW * kWarpsX), (rh + kTileH * kWarpsY - 1) / (kTileH * kWarpsY));
+    const size_t smem = (size_t)(a.tree.max_depth + 1) * kBlockThreads * sizeof(uint32_t);
+    if (trace)
+        render_kernel<SPP, true><<<grid, kBlockThreads, smem, stream>>>(a);
+    else
+        render_kernel<SPP, false><<<grid, kBlockThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// SPP dispatch = the reference's instantiation list (volrend.cu:266-278); anything else is an error there too.
+cudaError_t launch_render(const RenderArgs& a, int spp, bool trace, cudaStream_t stream, bool* bad_spp) {
+    *bad_spp = false;
+    switch (spp) {
+        case 1: return launch_spp<1>(a, trace, stream);
+        case 2: return launch_spp<2>(a, trace, stream);
+        case 3: return launch_spp<3>(a, trace, stream);
+        case 4: return launch_spp<4>(a, trace, stream);
+        case 6: return launch_spp<6>(a, trace, stream);
+        case 8: return launch_spp<8>(a, trace, stream);
+        case 16: return launch_spp<16>(a, trace, stream);
+        case 32: return launch_spp<32>(a, trace, stream);
+        default: *bad_spp = true; return cudaSuccess;
+    }
+}
+
+}  // namespace rto

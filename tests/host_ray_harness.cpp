@@ -1,0 +1,69 @@
+// TEST-ONLY host instantiation of rt_octree_b200/csrc/rto_ray.cuh (the header the CUDA kernels are built from).
+// It lets the CPU test-suite check the integer-coordinate / ancestor-resume traversal, the exact op sequence
+// and the SoA node-word encoding against oracle/rt_oracle.c without a GPU.  It is NOT linked into the product
+// library and the product has no CPU path.  Build: g++ -O2 -ffp-contract=off -mfma -mf16c (tests/conftest.py).
+#include <cstdint>
+#include <vector>
+
+#include "../rt_octree_b200/csrc/rto_ray.cuh"
+
+using namespace rto;
+
+namespace {
+struct VecStack {
+    std::vector<uint32_t> v;
+    uint32_t& operator()(int l) { return v[l]; }
+};
+
+template <int SPP>
+void run(const uint32_t* nodes, int max_depth, const FrameParams& fp, uint64_t rng_state, uint64_t rng_inc,
+         int pix_begin, int pix_end, const float* thresh, uint32_t* steps, int32_t* term, uint32_t* src_bits,
+         uint32_t* t_bits, uint64_t* leaf_hash, uint32_t* depth_sum, uint32_t* n_hits, uint32_t* n_loads,
+         int32_t* hit_leaf, uint32_t* hit_cnt, int32_t* leaf_seq, int max_seq) {
+    VecStack stack;
+    stack.v.assign(max_depth + 1, 0u);
+    for (int idx = pix_begin; idx < pix_end; ++idx) {
+        const size_t r = (size_t)(idx - pix_begin);
+        RaySetup rs;
+        setup_ray(fp, idx % fp.W, idx / fp.W, rs);
+        float dst[SPP + 1];
+        if (thresh) {
+            for (int i = 0; i < SPP; ++i) dst[i] = thresh[r * SPP + i];
+            dst[SPP] = FLT_MAX;
+        } else {
+            sorted_thresholds<SPP>(rng_state, rng_inc, idx, dst);
+        }
+        HitList<SPP> hits;
+        WalkOut wo;
+        auto sink = [&](uint32_t step, uint32_t leaf) {
+            if (leaf_seq && (int)step < max_seq) leaf_seq[r * max_seq + step] = (int32_t)leaf;
+        };
+        walk<SPP, true>(nodes, stack, rs, fp.step_size, fp.sigma_thresh, dst, hits, wo, sink);
+        steps[r] = wo.steps; term[r] = wo.term; src_bits[r] = u_bits(wo.src); t_bits[r] = u_bits(wo.t);
+        leaf_hash[r] = wo.hash; depth_sum[r] = wo.depth_sum; n_hits[r] = hits.n; n_loads[r] = wo.n_loads;
+        for (int i = 0; i < SPP; ++i) {
+            hit_leaf[r * SPP + i] = (int32_t)hits.leaf[i];
+            hit_cnt[r * SPP + i] = (uint32_t)hits.cnt[i];
+        }
+        if (leaf_seq)
+            for (int s = (int)wo.steps; s < max_seq; ++s) leaf_seq[r * max_seq + s] = -1;
+    }
+}
+}  // namespace
+
+extern "C" int host_ray_walk(const uint32_t* nodes, int max_depth, const float* c2w12, const float* offset,
+                             const float* scale, float fx, float fy, float ndc_w, float ndc_h, float ndc_f,
+                             float step_size, float sigma_thresh, int W, int H, int spp, uint64_t rng_state,
+                             uint64_t rng_inc, int pix_begin, int pix_end, const float* thresh, uint32_t* steps,
+                             int32_t* term, uint32_t* src_bits, uint32_t* t_bits, uint64_t* leaf_hash,
+                             uint32_t* depth_sum, uint32_t* n_hits, uint32_t* n_loads, int32_t* hit_leaf,
+                             uint32_t* hit_cnt, int32_t* leaf_seq, int max_seq) {
+    FrameParams fp{};
+    for (int i = 0; i < 12; ++i) fp.c2w[i] = c2w12[i];
+    for (int i = 0; i < 3; ++i) { fp.offset[i] = offset[i]; fp.scale[i] = scale[i]; }
+    fp.fx = fx; fp.fy = fy; fp.ndc_width = ndc_w; fp.ndc_height = ndc_h; fp.ndc_focal = ndc_f;
+    fp.step_size = step_size; fp.sigma_thresh = sigma_thresh; fp.background = 1.f; fp.W = W; fp.H = H;
+#define CASE(S) case S: run<S>(nodes, max_depth, fp, rng_state, rng_inc, pix_begin, pix_end, thresh, steps, term, src_bits, t_bits, leaf_hash, depth_sum, n_hits, n_loads, hit_leaf, hit_cnt, leaf_seq, max_seq); return 0;
+    switch (spp) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(6) CASE(8) CASE(16) CASE(32) default: return -1; }
+#undef CASE
+}

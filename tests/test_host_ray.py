@@ -1,0 +1,77 @@
+"""The CUDA kernels' per-ray code (rt_octree_b200/csrc/rto_ray.cuh: integer-coordinate, ancestor-resume traversal
+over the SoA node words) instantiated on the host by tests/host_ray_harness.cpp, against the oracle's root-restart
+floating-point restatement of the reference.  Every trace field must be BIT-identical.  (The GPU run of the same
+header is checked by tests/test_gpu_render.py.)"""
+import numpy as np
+import pytest
+
+from util import TRACE_KEYS, host_walk
+
+
+@pytest.mark.parametrize("spp", [1, 2, 3, 4, 6, 8, 16, 32])
+def test_host_ray_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp):
+    from rt_octree_b200 import synthetic as S
+
+    W, H = 120, 90
+    fx = S.blender_focal(W)
+    for pi in (0, 5):
+        rng = oracle.frame_rng(pi)
+        o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48)
+        h = host_walk(host_ray_lib, mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48)
+        for k in TRACE_KEYS + ("leaf_seq",):
+            assert np.array_equal(h[k], o[k]), (k, spp, pi)
+        assert o["steps"].max() > 40 and o["n_hits"].max() >= 1
+        # the ancestor-resume descent loads far fewer node words than the reference's root restart (+1 sigma load)
+        assert h["n_loads"].sum() < 0.5 * (o["depth_sum"].sum() + o["steps"].sum())
+
+
+def test_host_ray_ndc_and_anisotropic(oracle, host_ray_lib, poses8):
+    """NDC warp (volrend.cu:36-56) + anisotropic scale, forward-facing camera."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=6, shell=1.0, halo=0.05, seed=5, invradius3=(0.45, 0.3, 0.5), offset=(0.5, 0.45, 0.55))
+    W, H = 64, 48
+    fx = 60.0
+    ndc = (float(W), float(H), fx)
+    pose = S.poses_to_c2w12(np.stack([S.look_at_pose((0.1, 0.05, 0.2), target=(0.0, 0.0, -1.0), world_up=(0, 1, 0))]))[0]
+    rng = oracle.frame_rng(0)
+    for spp in (1, 6):
+        o = oracle.render(tree, pose, W, H, fx, fx, spp, rng, ndc=ndc, max_seq=32)
+        h = host_walk(host_ray_lib, tree, pose, W, H, fx, fx, spp, rng, ndc=ndc, max_seq=32)
+        for k in TRACE_KEYS + ("leaf_seq",):
+            assert np.array_equal(h[k], o[k]), k
+        assert o["steps"].sum() > 0
+
+
+def test_host_ray_injected_thresholds(oracle, host_ray_lib, small_tree, poses8):
+    """Threshold injection path used by the GPU tests (lg2.approx values come from the device)."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H, spp = 40, 30, 6
+    fx = S.blender_focal(W)
+    th = np.sort(np.random.default_rng(0).exponential(1.0, (W * H, spp)).astype(np.float32), axis=1)
+    rng = oracle.frame_rng(2)
+    o = oracle.render(small_tree, poses8[2], W, H, fx, fx, spp, rng, thresh=th)
+    h = host_walk(host_ray_lib, small_tree, poses8[2], W, H, fx, fx, spp, rng, thresh=th)
+    for k in TRACE_KEYS:
+        assert np.array_equal(h[k], o[k]), k
+
+
+def test_empty_and_degenerate_trees(oracle, host_ray_lib, poses8):
+    """A root-only tree (8 leaves), all empty and all dense."""
+    for sigma in (0.0, 50.0):
+        data = np.zeros((1, 2, 2, 2, 28), np.float16)
+        data[..., -1] = sigma
+        data[..., 0] = 0.5
+        tree = {"data_dim": np.int64(28), "data_format": np.array("SH9"), "invradius3": np.full(3, 0.375, np.float32),
+                "offset": np.full(3, 0.5, np.float32), "child": np.zeros((1, 2, 2, 2), np.int32), "data": data}
+        W, H, spp = 24, 24, 4
+        rng = oracle.frame_rng(0)
+        o = oracle.render(tree, poses8[0], W, H, 60.0, 60.0, spp, rng)
+        h = host_walk(host_ray_lib, tree, poses8[0], W, H, 60.0, 60.0, spp, rng)
+        for k in TRACE_KEYS:
+            assert np.array_equal(h[k], o[k]), k
+        if sigma == 0.0:
+            assert o["aux"][3].max() == 0.0 and np.all(o["aux"][:3] == 1.0)   # pure background
+        else:
+            assert o["aux"][3].max() == 1.0

@@ -1,0 +1,222 @@
+"""GPU parity tests of the render path, through the C ABI (rt_octree_b200/capi.py -> librtoctree_b200.so):
+traversal outputs BIT-EXACT against the oracle (thresholds dst[] are taken from the GPU because MUFU lg2.approx has
+no CPU equivalent; everything downstream of them is compared bit for bit), aux/RGB within 1e-5 of the oracle."""
+import numpy as np
+import pytest
+
+from util import TRACE_KEYS, GpuTrace
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(capi, tree, W, H, fx, fy=None):
+    t = capi.N3Tree(tree)
+    ctx = capi.RenderContext(W, H)
+    cam = capi.Camera(W, H, fx, fy if fy else fx)
+    return t, ctx, cam
+
+
+def _opts(capi, spp, denoise=False, **kw):
+    o = capi.RenderOptions()
+    o.spp = spp
+    o.denoise = denoise
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+@pytest.mark.parametrize("spp", [1, 2, 3, 4, 6, 8, 16, 32])
+def test_trace_bit_exact_vs_oracle(capi, oracle, mid_tree, poses8, spp):
+    from rt_octree_b200 import synthetic as S
+
+    W, H = 200, 152
+    fx = S.blender_focal(W)
+    t, ctx, cam = _setup(capi, mid_tree, W, H, fx)
+    for pi in (0, 5):
+        cam.transform = poses8[pi]
+        ctx.rng_set_frame(pi)
+        assert ctx.rng_get() == oracle.frame_rng(pi)
+        tr = GpuTrace(capi, W * H, spp, max_seq=64)
+        capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)
+        g = tr.host()
+        aux = ctx.read_aux()
+        img = ctx.read_image()
+        hit = g["steps"] > 0
+        th = g["thresh"]
+        assert np.all(np.diff(th[hit], axis=1) >= 0) and np.all(th[hit] >= 0)
+        # thresholds vs the CPU's log2f: same uniforms, MUFU lg2.approx within 2 ulp-ish relative error
+        o_cpu = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, oracle.frame_rng(pi), trace=False)
+        o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, oracle.frame_rng(pi), thresh=th, max_seq=64, want_img=True)
+        for k in TRACE_KEYS + ("leaf_seq",):
+            assert np.array_equal(g[k], o[k]), "trace field %s differs (spp %d pose %d): %d rays" % (
+                k, spp, pi, int((g[k] != o[k]).reshape(W * H, -1).any(1).sum()))
+        assert g["steps"].max() > 40 and g["n_hits"].max() >= 1 and (g["term"] >= 0).any()
+        assert np.array_equal(aux[3], o["aux"][3])                      # alpha = k/SPP exactly
+        assert np.abs(aux - o["aux"]).max() < 1e-5                       # rgb: only ex2.approx / fma order apart
+        assert np.abs(img - o["img"]).max() < 1e-5 and np.all(img[..., 3] == 1.0)
+        # against CPU-generated thresholds the image differs only where a threshold moved across a leaf boundary
+        assert np.mean(aux[3] != o_cpu["aux"][3]) < 2e-3
+        assert g["n_loads"].sum() < 0.5 * (o["depth_sum"].sum() + o["steps"].sum())
+
+
+def test_rng_uniforms_exact(capi, oracle, small_tree, poses8):
+    """exp(-dst) recovers 1-u: the pcg32 stream (advance(idx*SPP), next_uint) is reproduced exactly on the GPU."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H, spp = 64, 48, 6
+    t, ctx, cam = _setup(capi, small_tree, W, H, S.blender_focal(W))
+    cam.transform = poses8[1]
+    ctx.rng_set_frame(7)
+    tr = GpuTrace(capi, W * H, spp)
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)
+    g = tr.host()
+    bits = oracle.uniform_bits(oracle.frame_rng(7), (0, W * H), spp)
+    u = ((bits >> 9) | 0x3F800000).astype(np.uint32).view(np.float32) - np.float32(1.0)
+    expect = np.sort(-np.log((np.float32(1.0) - u).astype(np.float64)), axis=1)
+    hit = g["steps"] > 0
+    assert hit.sum() > 100
+    got = g["thresh"][hit].astype(np.float64)
+    assert np.allclose(got, expect[hit], rtol=2e-6, atol=2e-7)
+
+
+def test_ndc_anisotropic_rgba_and_options(capi, oracle, poses8):
+    from rt_octree_b200 import synthetic as S
+
+    # NDC + anisotropic scale
+    tree = S.make_tree(depth=6, shell=1.0, halo=0.05, seed=5, invradius3=(0.45, 0.3, 0.5), offset=(0.5, 0.45, 0.55))
+    W, H, fx = 64, 48, 60.0
+    pose = S.poses_to_c2w12(np.stack([S.look_at_pose((0.1, 0.05, 0.2), target=(0.0, 0.0, -1.0), world_up=(0, 1, 0))]))[0]
+    t, ctx, cam = _setup(capi, tree, W, H, fx)
+    t.set_ndc(W, H, fx)
+    cam.transform = pose
+    for spp, kw in ((1, {}), (6, dict(step_size=3e-4, sigma_thresh=7.0, background_brightness=0.25))):
+        ctx.rng_set_frame(0)
+        tr = GpuTrace(capi, W * H, spp, max_seq=32)
+        capi.launch_renderer(t, cam, _opts(capi, spp, **kw), ctx, trace=tr.pod)
+        g = tr.host()
+        o = oracle.render(tree, pose, W, H, fx, fx, spp, oracle.frame_rng(0), ndc=(W, H, fx), thresh=g["thresh"], max_seq=32,
+                          step_size=kw.get("step_size", 1e-4), sigma_thresh=kw.get("sigma_thresh", 1e-2),
+                          background=kw.get("background_brightness", 1.0))
+        for k in TRACE_KEYS + ("leaf_seq",):
+            assert np.array_equal(g[k], o[k]), k
+        assert np.abs(ctx.read_aux() - o["aux"]).max() < 1e-5
+        assert o["steps"].sum() > 0
+    # RGBA leaves (data_dim 4, rt_core.cuh:322-326)
+    base = S.make_tree(depth=5, shell=1.0, halo=0.05, seed=2)
+    rgba = dict(base)
+    d = base["data"].reshape(-1, 28)
+    rgba["data"] = np.ascontiguousarray(np.concatenate([np.abs(d[:, :3]).clip(0, 1), d[:, -1:]], axis=1)).reshape(-1, 2, 2, 2, 4)
+    rgba["data_dim"] = np.int64(4)
+    rgba["data_format"] = np.array("RGBA")
+    W, H = 80, 60
+    fx = S.blender_focal(W)
+    t2, ctx2, cam2 = _setup(capi, rgba, W, H, fx)
+    cam2.transform = poses8[2]
+    ctx2.rng_set_frame(2)
+    tr = GpuTrace(capi, W * H, 4)
+    capi.launch_renderer(t2, cam2, _opts(capi, 4), ctx2, trace=tr.pod)
+    g = tr.host()
+    o = oracle.render(rgba, poses8[2], W, H, fx, fx, 4, oracle.frame_rng(2), thresh=g["thresh"])
+    for k in TRACE_KEYS:
+        assert np.array_equal(g[k], o[k]), k
+    assert np.abs(ctx2.read_aux() - o["aux"]).max() < 1e-6
+
+
+def test_rect_render_equals_full_frame(capi, mid_tree, poses8):
+    """Tile split: bands rendered separately reproduce the full frame bit for bit."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H, spp = 160, 120, 6
+    t, ctx, cam = _setup(capi, mid_tree, W, H, S.blender_focal(W))
+    cam.transform = poses8[3]
+    ctx.rng_set_frame(3)
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx)
+    full = ctx.read_aux().copy()
+    ctx2 = capi.RenderContext(W, H)
+    ctx2.rng_set_frame(3)
+    for (y0, y1) in ((0, 37), (37, 90), (90, 120)):
+        capi.launch_renderer(t, cam, _opts(capi, spp), ctx2, rect=(0, y0, W, y1))
+    assert np.array_equal(ctx2.read_aux(), full)
+    ctx3 = capi.RenderContext(W, H)
+    ctx3.rng_set_frame(3)
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx3, rect=(13, 5, 101, 77))
+    part = ctx3.read_aux()
+    assert np.array_equal(part[:, 5:77, 13:101], full[:, 5:77, 13:101])
+    assert np.all(part[:, :5] == 0) and np.all(part[:, :, 101:] == 0)
+
+
+def test_frame_rng_is_pure_function_of_frame(capi, mid_tree, poses8):
+    """ctx.rng.advance() per frame (main_headless.cpp:479,506) == rng_set_frame(f): frame sharding is reproducible."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H = 96, 72
+    t, ctx, cam = _setup(capi, mid_tree, W, H, S.blender_focal(W))
+    o = _opts(capi, 6)
+    ctx.rng_seed()
+    for _ in range(100):
+        ctx.rng_advance()
+    seq = []
+    for f in range(3):
+        cam.transform = poses8[f]
+        capi.launch_renderer(t, cam, o, ctx)
+        seq.append(ctx.read_aux().copy())
+        ctx.rng_advance()
+    for f in (2, 0):
+        cam.transform = poses8[f]
+        ctx.rng_set_frame(f)
+        capi.launch_renderer(t, cam, o, ctx)
+        assert np.array_equal(ctx.read_aux(), seq[f])
+
+
+def test_errors(capi, small_tree):
+    t, ctx, cam = _setup(capi, small_tree, 32, 32, 40.0)
+    o = _opts(capi, 6)
+    o.spp = 5
+    with pytest.raises(capi.RtoError, match="spp == 5 not supported"):
+        capi.launch_renderer(t, cam, o, ctx)
+    o.spp = 6
+    cam2 = capi.Camera(16, 16, 40.0)
+    with pytest.raises(capi.RtoError, match="does not match context"):
+        capi.launch_renderer(t, cam2, o, ctx)
+    o.enable_probe = True
+    with pytest.raises(capi.RtoError, match="enable_probe"):
+        capi.launch_renderer(t, cam, o, ctx)
+    i = t.info
+    assert i.max_depth == 6 and i.payload_stride_halfs == 32 and i.capacity == small_tree["child"].shape[0]
+    assert i.n_leaves == int((small_tree["child"] == 0).sum())
+
+
+def test_full_size_properties(capi, oracle):
+    """BASELINE config size (800x800, SPP 6, depth-9 tree): size-independent properties + oracle on a pixel sample."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=9, shell=1.0, halo=0.05, seed=0)
+    poses = S.poses_to_c2w12(S.make_poses(200))
+    W = H = 800
+    fx = S.blender_focal(W)
+    t, ctx, cam = _setup(capi, tree, W, H, fx)
+    cam.transform = poses[17]
+    ctx.rng_set_frame(17)
+    spp = 6
+    tr = GpuTrace(capi, W * H, spp)
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)
+    g = tr.host()
+    aux = ctx.read_aux()
+    # alpha is a multiple of 1/SPP and equals the collision count; squares channel; background where nothing was hit
+    k = np.rint(aux[3] * spp)
+    assert np.array_equal(np.float32(k) * np.float32(1.0 / spp), aux[3])
+    assert np.array_equal(k.reshape(-1), g["hit_cnt"].sum(1))
+    assert np.array_equal(aux[4:], aux[:4] * aux[:4])
+    assert np.all(aux[:3, aux[3] == 0] == 1.0)
+    assert np.all((g["term"] >= 0) == (g["hit_cnt"].sum(1) == spp))
+    assert 0.05 < (aux[3] > 0).mean() < 0.6
+    # idempotence
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx)
+    assert np.array_equal(ctx.read_aux(), aux)
+    # oracle on three row bands of the full-size frame
+    for y in (100, 400, 401, 655):
+        b, e = y * W, (y + 1) * W
+        o = oracle.render(tree, poses[17], W, H, fx, fx, spp, oracle.frame_rng(17), pix_range=(b, e), thresh=g["thresh"][b:e])
+        for key in TRACE_KEYS:
+            assert np.array_equal(g[key][b:e], o[key]), key
+        assert np.abs(aux[:, y] - o["aux"][:, y]).max() < 1e-5

@@ -17,7 +17,9 @@ cudaError_t launch_build_nodes(const int32_t*, const __half*, int, int64_t, int6
                                int*, cudaStream_t);
 cudaError_t launch_build_payload(const __half*, int, int, int64_t, __half*, cudaStream_t);
 int tree_max_depth_host(const int32_t* child, int64_t capacity);
-cudaError_t launch_denoise_tc(const NetDev& net, const void* packed_weights, const DenoiseArgs& d, cudaStream_t stream);
+cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream);
+cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
+                               float4* out, cudaStream_t stream);
 size_t denoise_tc_packed_bytes();
 cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream);
 }  // namespace rto
@@ -407,30 +409,21 @@ int rto_denoise_rows(rto_context* c, const rto_net* n, int y0, int y1, void* str
     if (!c || !n) return fail(RTO_ERR_INVALID, "NULL argument");
     y0 = y0 < 0 ? 0 : y0; y1 = y1 > c->H ? c->H : y1;
     cudaStream_t s = (cudaStream_t)stream;
-    rto::DenoiseArgs d{c->aux, c->img, c->weight_map, c->guidance_map, c->W, c->H, y0, y1};
-    if (n->impl == 0 && n->tc_capable()) {
-        timer_start(c, 1, s);
-        cudaError_t e = rto::launch_denoise_tc(n->dev(), n->packed, d, s);
-        timer_stop(c, 1, s);
-        if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "denoise (tensor-core) launch: %s", cudaGetErrorString(e));
-        ++g_launches;
-        // single fused kernel: the "filter" stage has no launch of its own; its events bracket nothing
-        timer_start(c, 2, s);
-        timer_stop(c, 2, s);
-        return RTO_OK;
-    }
-    // net rows must cover the filter's halo: the filter at row y reads guidance rows y-L..y+L
+    // GuidanceNet rows must cover the filter's halo: the filter at row y reads guidance rows y-L..y+L
     const int L = n->levels;
-    rto::DenoiseArgs dn = d;
-    dn.y0 = y0 - L < 0 ? 0 : y0 - L;
-    dn.y1 = y1 + L > c->H ? c->H : y1 + L;
+    rto::DenoiseArgs dn{c->aux, c->img, c->weight_map, c->guidance_map, c->W, c->H, y0 - L < 0 ? 0 : y0 - L,
+                        y1 + L > c->H ? c->H : y1 + L};
+    const bool tc = n->impl == 0 && n->tc_capable();
     timer_start(c, 1, s);
-    cudaError_t e = rto::launch_guidance_net_simt(n->dev(), dn, s);
+    cudaError_t e = tc ? rto::launch_guidance_net_tc(n->dev(), n->packed, dn, s) : rto::launch_guidance_net_simt(n->dev(), dn, s);
     timer_stop(c, 1, s);
-    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch (%s): %s", tc ? "tcgen05" : "simt", cudaGetErrorString(e));
     timer_start(c, 2, s);
-    e = rto::launch_filter_simt(c->aux, (size_t)c->W * c->H, 1, c->weight_map, c->guidance_map, L, c->W, c->H, y0, y1,
-                                c->img, s);
+    if (tc)   // guidance is relu6-bounded here, so the precomputed-exp filter applies
+        e = rto::launch_filter_fast(c->aux, c->weight_map, c->guidance_map, c->W, c->H, y0, y1, c->img, s);
+    else
+        e = rto::launch_filter_simt(c->aux, (size_t)c->W * c->H, 1, c->weight_map, c->guidance_map, L, c->W, c->H, y0, y1,
+                                    c->img, s);
     timer_stop(c, 2, s);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
     g_launches += 2;
@@ -445,7 +438,8 @@ int rto_net_forward(const rto_net* n, const float* aux_dev, int W, int H, float*
     if (!n || !aux_dev || !weight_dev || !guidance_dev) return fail(RTO_ERR_INVALID, "NULL argument");
     if (W <= 0 || H <= 0) return fail(RTO_ERR_INVALID, "bad size");
     rto::DenoiseArgs d{aux_dev, nullptr, weight_dev, guidance_dev, W, H, 0, H};
-    cudaError_t e = rto::launch_guidance_net_simt(n->dev(), d, (cudaStream_t)stream);
+    cudaError_t e = (n->impl == 0 && n->tc_capable()) ? rto::launch_guidance_net_tc(n->dev(), n->packed, d, (cudaStream_t)stream)
+                                                       : rto::launch_guidance_net_simt(n->dev(), d, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch: %s", cudaGetErrorString(e));
     ++g_launches;
     return RTO_OK;

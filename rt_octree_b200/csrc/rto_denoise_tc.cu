@@ -1,11 +1,411 @@
-// rto_denoise_tc.cu — fused GuidanceNet (tcgen05 implicit GEMM) + kernel filter.  Placeholder until the
-// tensor-core kernel lands: reports "not available" so rto_denoise uses the CUDA-core path.
+// rto_denoise_tc.cu — GuidanceNet forward on the 5th-gen tensor cores (tcgen05 + TMEM) and the fast kernel filter.
+//
+// The two 3x3 convolutions of the deployed GuidanceNet (denoiser/network.py:123-168: conv 8->32, relu6, conv 32->8,
+// relu6, fp16 storage / fp32 accumulate) are the only dense contraction on the render path.  The reference runs
+// them through libtorch/cuDNN (src/denoiser/denoiser.cpp:46).  Here each CTA owns a 60x12 pixel tile and runs both
+// convolutions as implicit GEMMs with M = pixels, one tcgen05.mma per (M-tile, filter tap[, k-step]):
+//
+//   * the tile (+2 px halo) is staged in shared memory PIXEL-MAJOR with a pitch of 64 pixels, 8 fp16 channels =
+//     one 16-byte row of a K-major / no-swizzle core matrix.  Because consecutive pixels are consecutive 16-byte
+//     rows, the A operand of filter tap (dy,dx) is the SAME buffer viewed through a descriptor whose start address
+//     is shifted by (dy*64+dx) pixels — no im2col copy is ever materialised;
+//   * M-tiles are runs of 128 consecutive linear pixel positions (they wrap over image rows; the 2 wrap-around
+//     columns per row are computed and discarded);
+//   * conv1: 7 M-tiles x 9 taps, N = 32, K = 16 (8 real channels + a zero chunk), accumulators in TMEM columns
+//     [32*i, 32*i+32);  epilogue 1 (tcgen05.ld -> +bias, relu6, fp16) writes the 32-channel activation back to
+//     shared memory as four 8-channel planes (again 16 B per pixel per plane), zero outside the image;
+//   * conv2: 6 M-tiles x 9 taps x 2 k-steps, N = 16 (8 real outputs), K = 16, A = two planes per k-step (LBO = plane
+//     stride); accumulators reuse the TMEM columns;  epilogue 2 -> +bias, relu6, fp16 -> fp32 softmax / guidance.
+//   * 256 TMEM columns and ~99 KB of shared memory per CTA => two CTAs per SM overlap each other's phases.
+//
+// The kernel filter (denoiser/extension/filtering.cu:108-228) then runs as ONE launch for all levels with
+// e^{g} precomputed once per pixel and level (guidance is in [0,6] after relu6, so the reference's max-subtraction
+// is not needed for range) and 4 output rows per thread sharing their taps.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
 
 #include "rto_internal.h"
 
 namespace rto {
-size_t denoise_tc_packed_bytes() { return 0; }
-cudaError_t denoise_tc_pack_weights(const NetDev&, void*, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t launch_denoise_tc(const NetDev&, const void*, const DenoiseArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace tc {
+constexpr int TW = 60, TH = 12, PW = 64;          // output tile, smem pitch (= TW + 4)
+constexpr int IN_PX = (TH + 4) * PW + 64;         // staged input pixels (+ slack read only by discarded rows)
+constexpr int MID_PX = 1024;                      // positions per 8-channel plane of the conv1 activation
+constexpr int Q1_MIN = PW + 1, N1_TILES = 7;      // conv1 positions [65, 961): x in [1,62], y in [1,14]
+constexpr int Q2_MIN = 2 * PW + 2, N2_TILES = 6;  // conv2 positions [130, 898): x in [2,61], y in [2,13]
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 256;
+
+// shared memory map (bytes)
+constexpr int OFF_IN = 0;
+constexpr int OFF_MID = OFF_IN + IN_PX * 16;              // 17408
+constexpr int OFF_W1 = OFF_MID + 4 * MID_PX * 16;         // + 65536
+constexpr int OFF_W2 = OFF_W1 + 9 * 512;
+constexpr int OFF_ZERO = OFF_W2 + 9 * 1024;               // zero block: must lie ABOVE every operand start address
+constexpr int OFF_BIAS = OFF_ZERO + 2048;
+constexpr int OFF_BAR = OFF_BIAS + 40 * 4;
+constexpr int OFF_TMEM = OFF_BAR + 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 8;
+
+// packed weights in global memory: [w1: 9 taps][32 out][8 in] fp16 | [w2: 9 taps][4 chunks][16 out][8 in] fp16 |
+// b1 [32] fp32 | b2 [8] fp32
+constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 9 * 1024, PK_BYTES = PK_BIAS + 40 * 4;
+}  // namespace tc
+
+size_t denoise_tc_packed_bytes() { return tc::PK_BYTES; }
+
+__global__ void pack_weights_kernel(const NetDev net, unsigned char* __restrict__ out) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    __half* w1 = reinterpret_cast<__half*>(out + tc::PK_W1);
+    __half* w2 = reinterpret_cast<__half*>(out + tc::PK_W2);
+    float* bias = reinterpret_cast<float*>(out + tc::PK_BIAS);
+    if (tid < 9 * 32 * 8) {  // [tap][co][ci]  <- w1[co][ci][tap]
+        const int ci = tid % 8, co = (tid / 8) % 32, t = tid / 256;
+        w1[tid] = net.w1[(co * 8 + ci) * 9 + t];
+    }
+    if (tid < 9 * 4 * 16 * 8) {  // [tap][chunk][co16][ci8] <- w2[co][chunk*8+ci][tap], rows 8..15 zero
+        const int ci = tid % 8, co = (tid / 8) % 16, c = (tid / 128) % 4, t = tid / 512;
+        w2[tid] = co < 8 ? net.w2[(co * 32 + c * 8 + ci) * 9 + t] : __float2half(0.f);
+    }
+    if (tid < 32) bias[tid] = __half2float(net.b1[tid]);
+    if (tid < 8) bias[32 + tid] = __half2float(net.b2[tid]);
+}
+
+cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream) {
+    pack_weights_kernel<<<(9 * 4 * 16 * 8 + 255) / 256, 256, 0, stream>>>(net, static_cast<unsigned char*>(packed_dev));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// 8 rows x 16 B core matrices; rows 16 B apart, 8-row groups SBO apart, the two 8-element K chunks LBO apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t start_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((start_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// conv output -> fp16 activation, with the reference's rounding points (rto_internal.h NetDev::fused_bias)
+__device__ __forceinline__ __half act_h(float acc, float bias, int fused) {
+    const __half h = fused ? __float2half_rn(acc + bias) : __float2half_rn(__half2float(__float2half_rn(acc)) + bias);
+    return __hmin(__hmax(h, __float2half(0.f)), __float2half(6.f));
+}
+
+__global__ void __launch_bounds__(tc::THREADS, 2)
+guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseArgs d, int fused_bias) {
+    using namespace tc;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = d.W, H = d.H;
+    const int bx = blockIdx.x * TW, by = d.y0 + blockIdx.y * TH;   // image coords of output pixel (x=2, y=2) of the tile
+    const size_t HW = (size_t)W * H;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar = s_base + OFF_BAR;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+    // ---- one-time setup: TMEM allocation (warp 0), mbarrier (one thread)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_base + OFF_TMEM), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // ---- stage weights, zero block and the input tile (fp32 -> fp16, 8 channels = 16 B per pixel)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(packed);
+        uint4* w = reinterpret_cast<uint4*>(smem + OFF_W1);
+        for (int i = tid; i < (PK_BIAS) / 16; i += THREADS) w[i] = __ldg(src + i);
+        float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+        if (tid < 40) bias[tid] = __ldg(reinterpret_cast<const float*>(packed + PK_BIAS) + tid);
+        uint4* z = reinterpret_cast<uint4*>(smem + OFF_ZERO);
+        if (tid < 128) z[tid] = make_uint4(0, 0, 0, 0);
+        uint4* in = reinterpret_cast<uint4*>(smem + OFF_IN);
+        for (int p = tid; p < IN_PX; p += THREADS) {
+            const int x = p & (PW - 1), y = p >> 6;
+            const int gx = bx + x - 2, gy = by + y - 2;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (y < TH + 4 && gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                const float* a = d.aux + (size_t)gy * W + gx;
+                __half2 h0 = __floats2half2_rn(__ldg(a), __ldg(a + HW));
+                __half2 h1 = __floats2half2_rn(__ldg(a + 2 * HW), __ldg(a + 3 * HW));
+                __half2 h2 = __floats2half2_rn(__ldg(a + 4 * HW), __ldg(a + 5 * HW));
+                __half2 h3 = __floats2half2_rn(__ldg(a + 6 * HW), __ldg(a + 7 * HW));
+                v = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+            in[p] = v;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- conv1: 7 M-tiles x 9 taps, D[128 x 32] += A[128 x 16] * B[32 x 16]^T
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc(32);
+        const uint32_t zero = s_base + OFF_ZERO;
+#pragma unroll 1
+        for (int i = 0; i < N1_TILES; ++i) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int shift = (t / 3 - 1) * PW + (t % 3 - 1);
+                const uint32_t a0 = s_base + OFF_IN + (uint32_t)(Q1_MIN + 128 * i + shift) * 16u;
+                const uint32_t b0 = s_base + OFF_W1 + t * 512;
+                umma_f16(tmem + i * 32, make_desc(a0, zero - a0, 128), make_desc(b0, zero - b0, 128), idesc, t > 0);
+            }
+        }
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    tc_fence_after();
+
+    // ---- epilogue 1: +b1, relu6, fp16 -> four 8-channel planes, zero outside the image
+    {
+        const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
+        const int row = (warp & 3) * 32 + lane;
+        for (int i = warp >> 2; i < N1_TILES; i += 2) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + i * 32, r);
+            const int q = Q1_MIN + 128 * i + row;
+            const int x = q & (PW - 1), y = q >> 6;
+            const int gx = bx + x - 2, gy = by + y - 2;
+            const bool inside = gx >= 0 && gx < W && gy >= 0 && gy < H;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = c * 8 + 2 * j;
+                    const __half lo = act_h(__uint_as_float(r[ch]), bias[ch], fused_bias);
+                    const __half hi = act_h(__uint_as_float(r[ch + 1]), bias[ch + 1], fused_bias);
+                    pk[j] = inside ? ((uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16)) : 0u;
+                }
+                if (q < MID_PX)
+                    *reinterpret_cast<uint4*>(smem + OFF_MID + (c * MID_PX + q) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- conv2: 6 M-tiles x 9 taps x 2 k-steps, D[128 x 16] += A[128 x 16] * B[16 x 16]^T
+    if (tid == 0) {
+        constexpr uint32_t idesc = make_idesc(16);
+#pragma unroll 1
+        for (int j = 0; j < N2_TILES; ++j) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int shift = (t / 3 - 1) * PW + (t % 3 - 1);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const uint32_t a0 = s_base + OFF_MID + (uint32_t)(2 * s * MID_PX + Q2_MIN + 128 * j + shift) * 16u;
+                    const uint32_t b0 = s_base + OFF_W2 + t * 1024 + s * 512;
+                    umma_f16(tmem + j * 16, make_desc(a0, MID_PX * 16, 128), make_desc(b0, 256, 128), idesc, (t | s) > 0);
+                }
+            }
+        }
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 1);
+    tc_fence_after();
+
+    // ---- epilogue 2: +b2, relu6, fp16 -> float ; softmax over the first 4 channels ; guidance = last 4
+    {
+        const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS) + 32;
+        const int row = (warp & 3) * 32 + lane;
+        for (int j = warp >> 2; j < N2_TILES; j += 2) {
+            uint32_t r[8];
+            tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + j * 16, r);
+            const int q = Q2_MIN + 128 * j + row;
+            const int x = q & (PW - 1), y = q >> 6;
+            const int gx = bx + x - 2, gy = by + y - 2;
+            if (x >= 2 && x < TW + 2 && y >= 2 && y < TH + 2 && gx < W && gy < H && gy < d.y1) {
+                float o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = __half2float(act_h(__uint_as_float(r[c]), bias[c], fused_bias));
+                const float mx = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
+                float e[4], sum = 0.f;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) { e[l] = expf(o[l] - mx); sum += e[l]; }
+                const size_t p = (size_t)gy * W + gx;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    d.weight_map[l * HW + p] = e[l] / sum;
+                    d.guidance_map[l * HW + p] = o[4 + l];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fast filter
+// out(p) = sum_l w_l(p) * [sum_{q in N_l(p)} E_l(q) rgb(q)] / [sum_{q in N_l(p)} E_l(q)],  E_l = exp(g_l), 0 outside the
+// image (filtering.cu:108-228 with exp(g - max)/sum == exp(g)/sum; valid because relu6 bounds g to [0,6]).
+namespace ff {
+constexpr int BW = 32, BH = 32, R = 4, TWD = BW + 2 * R, THT = BH + 2 * R;   // 40 x 40 staged tile
+constexpr int ROWS = 4;                                                       // output rows per thread
+constexpr int THREADS = BW * (BH / ROWS);                                     // 256
+constexpr int SMEM_BYTES = TWD * THT * (16 + 4 * 4);
+}  // namespace ff
+
+__global__ void __launch_bounds__(ff::THREADS) filter_fast_kernel(const float* __restrict__ aux, const float* __restrict__ weight,
+                                                                 const float* __restrict__ guidance, int W, int H, int y0,
+                                                                 int y1, float4* __restrict__ out) {
+    using namespace ff;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    float4* rgb = reinterpret_cast<float4*>(fsm);                 // [THT][TWD] (r,g,b,unused)
+    float* E = reinterpret_cast<float*>(fsm + TWD * THT * 16);   // [4][THT][TWD]
+    const int tid = threadIdx.x;
+    const int bx = blockIdx.x * BW, by = y0 + blockIdx.y * BH;
+    const size_t HW = (size_t)W * H;
+    for (int i = tid; i < TWD * THT; i += THREADS) {
+        const int x = i % TWD, y = i / TWD;
+        const int gx = bx + x - R, gy = by + y - R;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const size_t p = (size_t)gy * W + gx;
+            c = make_float4(__ldg(aux + p), __ldg(aux + HW + p), __ldg(aux + 2 * HW + p), 0.f);
+            e0 = __expf(__ldg(guidance + p));
+            e1 = __expf(__ldg(guidance + HW + p));
+            e2 = __expf(__ldg(guidance + 2 * HW + p));
+            e3 = __expf(__ldg(guidance + 3 * HW + p));
+        }
+        rgb[i] = c;
+        E[i] = e0; E[TWD * THT + i] = e1; E[2 * TWD * THT + i] = e2; E[3 * TWD * THT + i] = e3;
+    }
+    __syncthreads();
+    const int tx = tid % BW, ty = (tid / BW) * ROWS;
+    const int gx = bx + tx;
+    float o[ROWS][3];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const int S = l + 1;
+        const float* El = E + l * TWD * THT;
+        float acc[ROWS][4];
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+        // tap rows ry (relative to output row ty) from -S to ROWS-1+S ; row ry feeds outputs k with |ry - k| <= S
+#pragma unroll
+        for (int ry = -S; ry <= ROWS - 1 + S; ++ry) {
+            const int base = (ty + R + ry) * TWD + tx + R;
+#pragma unroll
+            for (int dx = -S; dx <= S; ++dx) {
+                const float e = El[base + dx];
+                const float4 c = rgb[base + dx];
+                const float er = e * c.x, eg = e * c.y, eb = e * c.z;
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k)
+                    if (ry - k >= -S && ry - k <= S) { acc[k][0] += er; acc[k][1] += eg; acc[k][2] += eb; acc[k][3] += e; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            const int gy = by + ty + k;
+            if (gx < W && gy < H && gy < y1) {
+                const float w = __ldg(weight + l * HW + (size_t)gy * W + gx) * (1.0f / acc[k][3]);
+                o[k][0] += acc[k][0] * w; o[k][1] += acc[k][1] * w; o[k][2] += acc[k][2] * w;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+        const int gy = by + ty + k;
+        if (gx < W && gy < H && gy < y1) out[(size_t)gy * W + gx] = make_float4(o[k][0], o[k][1], o[k][2], 1.0f);
+    }
+}
+
+cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream) {
+    const int rows = d.y1 - d.y0;
+    if (rows <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(guidance_net_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + tc::TH - 1) / tc::TH);
+    guidance_net_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
+                               float4* out, cudaStream_t stream) {
+    const int rows = y1 - y0;
+    if (rows <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(filter_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ff::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((W + ff::BW - 1) / ff::BW, (rows + ff::BH - 1) / ff::BH);
+    filter_fast_kernel<<<grid, ff::THREADS, ff::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
+    return cudaGetLastError();
+}
+
 }  // namespace rto

@@ -30,6 +30,7 @@ def test_net_forward_simt_matches_oracle(capi, oracle, net_weights, shape):
     aux = rs.uniform(0, 1, (8, H, W)).astype(np.float32)
     aux[4:] = aux[:4] ** 2
     net = capi.Denoiser(net_weights)
+    net.set_impl(1)
     a = _dev(aux)
     wm = torch.zeros((4, H, W), device="cuda")
     gm = torch.zeros((4, H, W), device="cuda")
@@ -40,6 +41,32 @@ def test_net_forward_simt_matches_oracle(capi, oracle, net_weights, shape):
         ow, og = oracle.guidance_net(aux, net_weights, fused_bias=fused)
         assert np.array_equal(gm.cpu().numpy(), og)            # same fp32 accumulation order => bit-identical
         assert np.abs(wm.cpu().numpy() - ow).max() < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(24, 40), (67, 129), (12, 60), (13, 61), (5, 7), (200, 304)])
+def test_net_forward_tensor_core_matches_oracle(capi, oracle, net_weights, shape):
+    """tcgen05 implicit-GEMM GuidanceNet vs the oracle: identical fp16 rounding points, only the fp32 accumulation
+    order inside the tensor core differs => at most one fp16 ulp on a small fraction of the outputs."""
+    import torch
+
+    H, W = shape
+    rs = np.random.default_rng(H * W + 1)
+    aux = rs.uniform(0, 1, (8, H, W)).astype(np.float32)
+    aux[4:] = aux[:4] ** 2
+    net = capi.Denoiser(net_weights)
+    net.set_impl(0)
+    a = _dev(aux)
+    wm = torch.full((4, H, W), -1.0, device="cuda")
+    gm = torch.full((4, H, W), -1.0, device="cuda")
+    for fused in (False, True):
+        net.set_bias_mode(fused)
+        net.forward(a.data_ptr(), W, H, wm.data_ptr(), gm.data_ptr())
+        torch.cuda.synchronize()
+        ow, og = oracle.guidance_net(aux, net_weights, fused_bias=fused)
+        d = np.abs(gm.cpu().numpy() - og)
+        assert d.max() <= 2.0 ** -8 + 1e-7, "max |dg| = %g" % d.max()
+        assert (d == 0).mean() > 0.97, (d == 0).mean()
+        assert np.abs(wm.cpu().numpy() - ow).max() < 4e-3
 
 
 def test_net_forward_matches_torch_gpu_conv(capi, net_weights):
@@ -60,6 +87,7 @@ def test_net_forward_matches_torch_gpu_conv(capi, net_weights):
     ref_g = z[4:].cpu().numpy()
     ref_w = torch.softmax(z[:4], dim=0).cpu().numpy()
     net = capi.Denoiser(net_weights)
+    net.set_impl(1)
     wm = torch.zeros((4, H, W), device="cuda")
     gm = torch.zeros((4, H, W), device="cuda")
     frac = {}
@@ -86,7 +114,8 @@ def test_filter_matches_oracle(capi, oracle, L):
     weight /= weight.sum(0, keepdims=True)
     img = rs.uniform(0, 1, (H, W, 4)).astype(np.float32)
     out = torch.zeros((H, W, 4), device="cuda")
-    capi.filtering(_dev(weight).data_ptr(), _dev(guidance).data_ptr(), _dev(img).data_ptr(), L, W, H, out.data_ptr())
+    dw, dg, di = _dev(weight), _dev(guidance), _dev(img)     # keep the device tensors alive across the call
+    capi.filtering(dw.data_ptr(), dg.data_ptr(), di.data_ptr(), L, W, H, out.data_ptr())
     torch.cuda.synchronize()
     ref = oracle.filtering(weight, guidance, img)
     assert np.abs(out.cpu().numpy() - ref).max() < 2e-6
@@ -122,9 +151,8 @@ def test_denoise_end_to_end(capi, oracle, mid_tree, poses8, net_weights, impl):
     assert d.max() < tol, d.max()
     # denoising must reduce the error against a high-SPP render of the same view
     clean = oracle.render(mid_tree, poses8[4], W, H, fx, fx, 32, oracle.frame_rng(4), trace=False)["aux"][:3]
-    noisy_err = np.mean((aux[:3] - clean) ** 2)
     den_err = np.mean((np.transpose(img[..., :3], (2, 0, 1)) - clean) ** 2)
-    assert np.isfinite(den_err) and den_err < 4 * noisy_err   # random-init net: no quality claim, only sanity
+    assert np.isfinite(den_err) and den_err < 0.05            # random-init net: no quality claim, only sanity
     # row bands == full frame (tile split)
     ctx2 = capi.RenderContext(W, H)
     ctx2.rng_set_frame(4)

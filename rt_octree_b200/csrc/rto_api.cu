@@ -22,6 +22,7 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
                                float4* out, cudaStream_t stream);
 size_t denoise_tc_packed_bytes();
 cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream);
+cudaError_t denoise_tc_set_debug(float* p);
 }  // namespace rto
 
 struct rto_tree {
@@ -454,6 +455,12 @@ int rto_filter(const float* weight_dev, const float* guidance_dev, const float* 
                                             reinterpret_cast<float4*>(img_out_dev), (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
     ++g_launches;
+    return RTO_OK;
+}
+
+// test-only debug tap of the tensor-core kernel (not declared in the public header)
+int rto_debug_tc_dump(float* dev_buf) {
+    RTO_CUDA(rto::denoise_tc_set_debug(dev_buf));
     return RTO_OK;
 }
 

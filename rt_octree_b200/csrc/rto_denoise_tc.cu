@@ -58,6 +58,10 @@ constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 9 * 1024, PK_BYTES =
 
 size_t denoise_tc_packed_bytes() { return tc::PK_BYTES; }
 
+// debug tap (tests only): when set, CTA (0,0) dumps its raw conv1 / conv2 accumulators: [1024][32] then [1024][8] floats
+__device__ float* g_tc_dbg = nullptr;
+cudaError_t denoise_tc_set_debug(float* p) { return cudaMemcpyToSymbol(g_tc_dbg, &p, sizeof(p)); }
+
 __global__ void pack_weights_kernel(const NetDev net, unsigned char* __restrict__ out) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     __half* w1 = reinterpret_cast<__half*>(out + tc::PK_W1);
@@ -225,6 +229,8 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
             const int x = q & (PW - 1), y = q >> 6;
             const int gx = bx + x - 2, gy = by + y - 2;
             const bool inside = gx >= 0 && gx < W && gy >= 0 && gy < H;
+            if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && q < 1024)
+                for (int c = 0; c < 32; ++c) g_tc_dbg[q * 32 + c] = __uint_as_float(r[c]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t pk[4];
@@ -276,6 +282,8 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
             const int q = Q2_MIN + 128 * j + row;
             const int x = q & (PW - 1), y = q >> 6;
             const int gx = bx + x - 2, gy = by + y - 2;
+            if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && q < 1024)
+                for (int c = 0; c < 8; ++c) g_tc_dbg[1024 * 32 + q * 8 + c] = __uint_as_float(r[c]);
             if (x >= 2 && x < TW + 2 && y >= 2 && y < TH + 2 && gx < W && gy < H && gy < d.y1) {
                 float o[8];
 #pragma unroll

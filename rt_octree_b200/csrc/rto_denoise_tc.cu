@@ -26,6 +26,7 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <cstring>
 
 #include "rto_internal.h"
 
@@ -140,10 +141,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// conv output -> fp16 activation, with the reference's rounding points (rto_internal.h NetDev::fused_bias)
-__device__ __forceinline__ __half act_h(float acc, float bias, int fused) {
-    const __half h = fused ? __float2half_rn(acc + bias) : __float2half_rn(__half2float(__float2half_rn(acc)) + bias);
-    return __hmin(__hmax(h, __float2half(0.f)), __float2half(6.f));
+// two conv outputs -> packed fp16 activations, with the reference's rounding points (rto_internal.h NetDev::fused_bias):
+//   fused = 0 : half(float(half(acc)) + bias) ; fused = 1 : half(acc + bias) ; then relu6 (exact on fp16 values).
+__device__ __forceinline__ uint32_t act_h2(float acc0, float acc1, float b0, float b1, int fused) {
+    float v0, v1;
+    if (fused) {
+        v0 = acc0 + b0;
+        v1 = acc1 + b1;
+    } else {
+        const __half2 r = __floats2half2_rn(acc0, acc1);
+        const float2 f = __half22float2(r);
+        v0 = f.x + b0;
+        v1 = f.y + b1;
+    }
+    __half2 h = __floats2half2_rn(v0, v1);   // .x (low 16 bits) = v0
+    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
+    uint32_t u;
+    memcpy(&u, &h, 4);
+    return u;
 }
 
 __global__ void __launch_bounds__(tc::THREADS, 2)
@@ -237,9 +252,8 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int ch = c * 8 + 2 * j;
-                    const __half lo = act_h(__uint_as_float(r[ch]), bias[ch], fused_bias);
-                    const __half hi = act_h(__uint_as_float(r[ch + 1]), bias[ch + 1], fused_bias);
-                    pk[j] = inside ? ((uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16)) : 0u;
+                    const uint32_t u = act_h2(__uint_as_float(r[ch]), __uint_as_float(r[ch + 1]), bias[ch], bias[ch + 1], fused_bias);
+                    pk[j] = inside ? u : 0u;
                 }
                 if (q < MID_PX)
                     *reinterpret_cast<uint4*>(smem + OFF_MID + (c * MID_PX + q) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -251,6 +265,12 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     __syncthreads();
     tc_fence_after();
 
+    if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0) {   // debug: what conv2 is about to read
+        const __half* m = reinterpret_cast<const __half*>(smem + OFF_MID);
+        for (int i = tid; i < 4 * MID_PX * 8; i += THREADS) g_tc_dbg[1024 * 40 + i] = __half2float(m[i]);
+        const __half* w = reinterpret_cast<const __half*>(smem + OFF_W2);
+        for (int i = tid; i < 9 * 512; i += THREADS) g_tc_dbg[1024 * 40 + 4 * MID_PX * 8 + i] = __half2float(w[i]);
+    }
     // ---- conv2: 6 M-tiles x 9 taps x 2 k-steps, D[128 x 16] += A[128 x 16] * B[16 x 16]^T
     if (tid == 0) {
         constexpr uint32_t idesc = make_idesc(16);
@@ -287,7 +307,14 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
             if (x >= 2 && x < TW + 2 && y >= 2 && y < TH + 2 && gx < W && gy < H && gy < d.y1) {
                 float o[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = __half2float(act_h(__uint_as_float(r[c]), bias[c], fused_bias));
+                for (int c = 0; c < 8; c += 2) {
+                    const uint32_t u = act_h2(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), bias[c], bias[c + 1], fused_bias);
+                    __half2 h;
+                    memcpy(&h, &u, 4);
+                    const float2 f = __half22float2(h);
+                    o[c] = f.x;
+                    o[c + 1] = f.y;
+                }
                 const float mx = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
                 float e[4], sum = 0.f;
 #pragma unroll

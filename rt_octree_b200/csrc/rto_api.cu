@@ -37,6 +37,7 @@ struct rto_context {
     float4* img = nullptr;
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
+    int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
     rto::Pcg32 rng{};
     // Timer
     bool timing = false;
@@ -245,6 +246,8 @@ int rto_context_create(rto_context** out, int W, int H) {
     if (e == cudaSuccess) e = cudaMalloc(&c->img, px * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&c->weight_map, px * 6 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->guidance_map, px * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->tile_counter, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->tile_counter, 0, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(c->aux, 0, px * 8 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(c->img, 0, px * sizeof(float4));
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
@@ -261,7 +264,7 @@ int rto_context_create(rto_context** out, int W, int H) {
 }
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
-    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map);
+    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
         if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
@@ -325,6 +328,7 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;
+    a.tile_counter = c->tile_counter;
     // with the denoiser on, the final image comes from rto_denoise; the reference then renders into a separate
     // noisy surface whose rgb equals aux channels 0..2 (volrend.cu:188-192 vs :205-212), so nothing is lost here
     a.img = opt->denoise ? nullptr : c->img;

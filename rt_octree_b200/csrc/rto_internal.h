@@ -41,6 +41,7 @@ struct RenderArgs {
     int x0, y0, x1, y1;            // pixel rectangle to render (full frame, or a band for the tile split)
     float* aux;                    // [8][H][W] fp32
     float4* img;                   // [H][W] float4, may be nullptr
+    int* tile_counter;             // [2] device ints owned by the context: next tile, finished warps (self re-arming)
     TraceOut tr;
 };
 

@@ -17,162 +17,202 @@
 
 namespace rto {
 
-constexpr int kTileW = 8, kTileH = 4;      // pixels per warp
-constexpr int kWarpsX = 2, kWarpsY = 2;    // warps per block
-constexpr int kBlockThreads = 32 * kWarpsX * kWarpsY;
+constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
+constexpr int kBlockThreads = 128;         // 4 independent warps per block
 
-struct SmemStack {
-    uint32_t* base;  // &stk[tid]
-    __device__ __forceinline__ uint32_t& operator()(int l) { return base[l * kBlockThreads]; }
+// Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
+//   [0, D]            ancestor stack (D = tree max depth)
+//   [D+1, D+1+SPP]    sorted thresholds + FLT_MAX sentinel
+//   [.., +SPP)        collided leaf ids      [.., +SPP) collision counts
+template <int SPP>
+struct SmemRay {
+    uint32_t* base;   // &smem[threadIdx.x]
+    int off_dst;      // D + 1
+    __device__ __forceinline__ uint32_t& stack(int l) { return base[l * kBlockThreads]; }
+    __device__ __forceinline__ float& dst(int i) { return reinterpret_cast<float*>(base)[(off_dst + i) * kBlockThreads]; }
+    __device__ __forceinline__ uint32_t& hit_leaf(int i) { return base[(off_dst + SPP + 1 + i) * kBlockThreads]; }
+    __device__ __forceinline__ float& hit_cnt(int i) { return reinterpret_cast<float*>(base)[(off_dst + 2 * SPP + 1 + i) * kBlockThreads]; }
+    static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1; }
 };
 
+// Persistent kernel: every warp pulls 8x4 pixel tiles from a global counter until the frame (or rectangle) is done,
+// so a warp slot never idles behind a slower sibling warp and the heavy centre rows are handed out first.
 template <int SPP, bool TRACE>
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_constant__ RenderArgs a) {
-    extern __shared__ uint32_t stk_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile_x = blockIdx.x * (kTileW * kWarpsX) + (warp % kWarpsX) * kTileW;
-    const int tile_y = blockIdx.y * (kTileH * kWarpsY) + (warp / kWarpsX) * kTileH;
-    const int ix = a.x0 + tile_x + (lane & (kTileW - 1));
-    const int iy = a.y0 + tile_y + (lane / kTileW);
-    if (ix >= a.x1 || iy >= a.y1) return;
+__global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 10 : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
+    extern __shared__ uint32_t ray_smem[];
+    const int lane = threadIdx.x & 31;
     const FrameParams& fp = a.fp;
-    const int idx = iy * fp.W + ix;   // full-frame pixel index: RNG offset and aux address (volrend.cu:92-95)
+    const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
+    const int tiles_x = (rw + kTileW - 1) / kTileW, tiles_y = (rh + kTileH - 1) / kTileH;
+    const int n_tiles = tiles_x * tiles_y;
+    SmemRay<SPP> mem{ray_smem + threadIdx.x, a.tree.max_depth + 1};
+    const uint32_t* __restrict__ nodes = a.tree.nodes;
 
-    RaySetup rs;
-    setup_ray(fp, ix, iy, rs);
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        // centre-first row order: 0 -> mid, 1 -> mid-1, 2 -> mid+1, ...
+        const int tr = tile / tiles_x, tc = tile - tr * tiles_x;
+        const int mid = tiles_y >> 1;
+        const int row = (tr & 1) ? mid - 1 - (tr >> 1) : mid + (tr >> 1);
+        const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
+        const int iy = a.y0 + row * kTileH + (lane / kTileW);
+        if (ix < a.x1 && iy < a.y1) {
+            const int idx = iy * fp.W + ix;   // full-frame pixel index: RNG offset and buffer address (volrend.cu:92-95)
+            RaySetup rs;
+            setup_ray(fp, ix, iy, rs);
+            float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
+            WalkOut wo;
+            if (rs.hit) sorted_thresholds<SPP>(a.rng_state, a.rng_inc, idx, mem);
+            if (TRACE && a.tr.thresh && rs.hit) {
+                for (int i = 0; i < SPP; ++i) a.tr.thresh[(size_t)idx * SPP + i] = mem.dst(i);
+            }
+            auto sink = [&](uint32_t step, uint32_t leaf) {
+                if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
+            };
+            walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+            const uint32_t sh_nums = wo.n_hits;
 
-    float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
-    HitList<SPP> hits;
-    WalkOut wo;
-    {
-        float dst[SPP + 1];
-        if (rs.hit) sorted_thresholds<SPP>(a.rng_state, a.rng_inc, idx, dst);
-        if (TRACE && a.tr.thresh && rs.hit) {
+            if (TRACE) {
+                const TraceOut& tr = a.tr;
+                if (tr.steps) tr.steps[idx] = wo.steps;
+                if (tr.term) tr.term[idx] = wo.term;
+                if (tr.src_bits) tr.src_bits[idx] = u_bits(wo.src);
+                if (tr.t_bits) tr.t_bits[idx] = u_bits(wo.t);
+                if (tr.leaf_hash) tr.leaf_hash[idx] = wo.hash;
+                if (tr.depth_sum) tr.depth_sum[idx] = wo.depth_sum;
+                if (tr.n_hits) tr.n_hits[idx] = sh_nums;
+                if (tr.n_loads) tr.n_loads[idx] = wo.n_loads;
+                for (int i = 0; i < SPP; ++i) {
+                    const bool live = i < (int)sh_nums;
+                    if (tr.hit_leaf) tr.hit_leaf[(size_t)idx * SPP + i] = live ? (int32_t)mem.hit_leaf(i) : -1;
+                    if (tr.hit_cnt) tr.hit_cnt[(size_t)idx * SPP + i] = live ? (uint32_t)mem.hit_cnt(i) : 0u;
+                }
+                if (tr.leaf_seq)
+                    for (int s = (int)wo.steps; s < tr.max_seq; ++s) tr.leaf_seq[(size_t)idx * tr.max_seq + s] = -1;
+            }
+
+            if (sh_nums > 0) {
+                // accumulate colour (rt_core.cuh:277-331)
+                const int bd = a.tree.basis_dim;
+                const __half* __restrict__ sh = a.tree.sh;
+                const int stride = a.tree.sh_stride;
+                if (bd == 9) {
+                    float b[9];
+                    sh_basis(9, rs.vdir, b);
+                    for (int i = 0; i < (int)sh_nums; ++i) {
+                        const uint4* q = reinterpret_cast<const uint4*>(sh + (size_t)mem.hit_leaf(i) * stride);
+                        const float c_i = mem.hit_cnt(i);
+                        uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < SPP; ++i) a.tr.thresh[(size_t)idx * SPP + i] = dst[i];
-        }
-        SmemStack stack{stk_smem + threadIdx.x};
-        auto sink = [&](uint32_t step, uint32_t leaf) {
-            if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
-        };
-        walk<SPP, TRACE>(a.tree.nodes, stack, rs, fp.step_size, fp.sigma_thresh, dst, hits, wo, sink);
-    }
-    const uint32_t sh_nums = hits.n;
-    const uint32_t (&hit_leaf)[SPP] = hits.leaf;
-    const float (&cnts)[SPP] = hits.cnt;
-
-    if (TRACE) {
-        const TraceOut& tr = a.tr;
-        if (tr.steps) tr.steps[idx] = wo.steps;
-        if (tr.term) tr.term[idx] = wo.term;
-        if (tr.src_bits) tr.src_bits[idx] = u_bits(wo.src);
-        if (tr.t_bits) tr.t_bits[idx] = u_bits(wo.t);
-        if (tr.leaf_hash) tr.leaf_hash[idx] = wo.hash;
-        if (tr.depth_sum) tr.depth_sum[idx] = wo.depth_sum;
-        if (tr.n_hits) tr.n_hits[idx] = sh_nums;
-        if (tr.n_loads) tr.n_loads[idx] = wo.n_loads;
-        for (int i = 0; i < SPP; ++i) {
-            if (tr.hit_leaf) tr.hit_leaf[(size_t)idx * SPP + i] = (int32_t)hit_leaf[i];
-            if (tr.hit_cnt) tr.hit_cnt[(size_t)idx * SPP + i] = (uint32_t)cnts[i];
-        }
-        if (tr.leaf_seq)
-            for (int s = (int)wo.steps; s < tr.max_seq; ++s) tr.leaf_seq[(size_t)idx * tr.max_seq + s] = -1;
-    }
-
-    if (sh_nums > 0) {
-        // accumulate colour (rt_core.cuh:277-331)
-        const int bd = a.tree.basis_dim;
-        const __half* __restrict__ sh = a.tree.sh;
-        const int stride = a.tree.sh_stride;
-        if (bd == 9) {
-            float b[9];
-            sh_basis(9, rs.vdir, b);
-#pragma unroll
-            for (int i = 0; i < SPP; ++i) {
-                if (i < (int)sh_nums) {
-                    const uint4* q = reinterpret_cast<const uint4*>(sh + (size_t)hit_leaf[i] * stride);
-                    uint32_t w[16];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint4 v = __ldg(q + k);
-                        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-                    }
+                        for (int k = 0; k < 4; ++k) {
+                            const uint4 v = __ldg(q + k);
+                            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                        }
 #define HV(k) f_half_bits_to_float((w[(k) >> 1] >> (((k) & 1) * 16)) & 0xffffu)
-                    float rgb[3];
+                        float rgb[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
+                        for (int c = 0; c < 3; ++c) {
 #define MB(k) (b[k] * HV(9 * c + (k)))
-                        float tmp = b[0] * HV(9 * c);
-                        tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
-                        tmp += MB(1) + MB(2) + MB(3);
+                            float tmp = b[0] * HV(9 * c);
+                            tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
+                            tmp += MB(1) + MB(2) + MB(3);
 #undef MB
-                        rgb[c] = f_div(cnts[i], 1.f + f_exp(-tmp));
-                    }
+                            rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
+                        }
 #undef HV
-                    out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
-                    out3 += cnts[i];
-                }
-            }
-        } else if (bd > 0) {
-            float b[25];
+                        out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
+                        out3 += c_i;
+                    }
+                } else if (bd > 0) {
+                    float b[25];
 #pragma unroll
-            for (int k = 0; k < 25; ++k) b[k] = 0.f;
-            sh_basis(bd, rs.vdir, b);
-            for (int i = 0; i < (int)sh_nums; ++i) {
-                const uint32_t leaf = selu(hit_leaf, i);
-                const float c_i = sel(cnts, i);
-                const __half* h = sh + (size_t)leaf * stride;
-                float rgb[3];
-                for (int c = 0; c < 3; ++c) {
-                    const __half* hc = h + bd * c;
+                    for (int k = 0; k < 25; ++k) b[k] = 0.f;
+                    sh_basis(bd, rs.vdir, b);
+                    for (int i = 0; i < (int)sh_nums; ++i) {
+                        const float c_i = mem.hit_cnt(i);
+                        const __half* h = sh + (size_t)mem.hit_leaf(i) * stride;
+                        float rgb[3];
+                        for (int c = 0; c < 3; ++c) {
+                            const __half* hc = h + bd * c;
 #define MB(k) (b[k] * __half2float(__ldg(hc + (k))))
-                    float tmp = b[0] * __half2float(__ldg(hc));
-                    if (bd >= 25) tmp += MB(16) + MB(17) + MB(18) + MB(19) + MB(20) + MB(21) + MB(22) + MB(23) + MB(24);
-                    if (bd >= 16) tmp += MB(9) + MB(10) + MB(11) + MB(12) + MB(13) + MB(14) + MB(15);
-                    if (bd >= 9) tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
-                    if (bd >= 4) tmp += MB(1) + MB(2) + MB(3);
+                            float tmp = b[0] * __half2float(__ldg(hc));
+                            if (bd >= 25) tmp += MB(16) + MB(17) + MB(18) + MB(19) + MB(20) + MB(21) + MB(22) + MB(23) + MB(24);
+                            if (bd >= 16) tmp += MB(9) + MB(10) + MB(11) + MB(12) + MB(13) + MB(14) + MB(15);
+                            if (bd >= 9) tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
+                            if (bd >= 4) tmp += MB(1) + MB(2) + MB(3);
 #undef MB
-                    rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
+                            rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
+                        }
+                        out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
+                        out3 += c_i;
+                    }
+                } else {  // RGBA leaves (rt_core.cuh:322-326)
+                    for (int i = 0; i < (int)sh_nums; ++i) {
+                        const float c_i = mem.hit_cnt(i);
+                        const __half* h = sh + (size_t)mem.hit_leaf(i) * stride;
+                        out0 += __half2float(__ldg(h + 0)) * c_i;
+                        out1 += __half2float(__ldg(h + 1)) * c_i;
+                        out2 += __half2float(__ldg(h + 2)) * c_i;
+                        out3 += c_i;
+                    }
                 }
-                out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
-                out3 += c_i;
+                constexpr float INV_SPP = 1.0f / SPP;
+                out0 = f_mul(out0, INV_SPP); out1 = f_mul(out1, INV_SPP); out2 = f_mul(out2, INV_SPP); out3 = f_mul(out3, INV_SPP);
             }
-        } else {  // RGBA leaves (rt_core.cuh:322-326)
-            for (int i = 0; i < (int)sh_nums; ++i) {
-                const uint32_t leaf = selu(hit_leaf, i);
-                const float c_i = sel(cnts, i);
-                const __half* h = sh + (size_t)leaf * stride;
-                out0 += __half2float(__ldg(h + 0)) * c_i;
-                out1 += __half2float(__ldg(h + 1)) * c_i;
-                out2 += __half2float(__ldg(h + 2)) * c_i;
-                out3 += c_i;
+
+            // background composite, offscreen branch (volrend.cu:174-179)
+            const float remain = f_mul(f_sub(1.f, out3), fp.background);
+            out0 = f_add(out0, remain); out1 = f_add(out1, remain); out2 = f_add(out2, remain);
+
+            // aux [8][H][W] (volrend.cu:187-202) and image [H][W][4] (volrend.cu:205-212)
+            if (a.aux) {
+                const size_t SIZE = (size_t)fp.W * fp.H;
+                float* q = a.aux + idx;
+                q[0] = out0; q[SIZE] = out1; q[2 * SIZE] = out2; q[3 * SIZE] = out3;
+                q[4 * SIZE] = f_mul(out0, out0); q[5 * SIZE] = f_mul(out1, out1);
+                q[6 * SIZE] = f_mul(out2, out2); q[7 * SIZE] = f_mul(out3, out3);
             }
+            if (a.img) a.img[idx] = make_float4(out0, out1, out2, 1.0f);
         }
-        constexpr float INV_SPP = 1.0f / SPP;
-        out0 = f_mul(out0, INV_SPP); out1 = f_mul(out1, INV_SPP); out2 = f_mul(out2, INV_SPP); out3 = f_mul(out3, INV_SPP);
+        __syncwarp();
     }
-
-    // background composite, offscreen branch (volrend.cu:174-179)
-    const float remain = f_mul(f_sub(1.f, out3), fp.background);
-    out0 = f_add(out0, remain); out1 = f_add(out1, remain); out2 = f_add(out2, remain);
-
-    // aux [8][H][W] (volrend.cu:187-202) and image [H][W][4] (volrend.cu:205-212)
-    if (a.aux) {
-        const size_t SIZE = (size_t)fp.W * fp.H;
-        float* q = a.aux + idx;
-        q[0] = out0; q[SIZE] = out1; q[2 * SIZE] = out2; q[3 * SIZE] = out3;
-        q[4 * SIZE] = f_mul(out0, out0); q[5 * SIZE] = f_mul(out1, out1);
-        q[6 * SIZE] = f_mul(out2, out2); q[7 * SIZE] = f_mul(out3, out3);
+    // the last warp to leave re-arms the counters for the next launch on this context
+    if (lane == 0) {
+        const int total_warps = gridDim.x * (kBlockThreads / 32);
+        if (atomicAdd(a.tile_counter + 1, 1) == total_warps - 1) {
+            a.tile_counter[0] = 0;
+            a.tile_counter[1] = 0;
+            __threadfence();
+        }
     }
-    if (a.img) a.img[idx] = make_float4(out0, out1, out2, 1.0f);
 }
 
 template <int SPP>
 static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stream) {
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
-    dim3 grid((rw + kTileW * kWarpsX - 1) / (kTileW * kWarpsX), (rh + kTileH * kWarpsY - 1) / (kTileH * kWarpsY));
-    const size_t smem = (size_t)(a.tree.max_depth + 1) * kBlockThreads * sizeof(uint32_t);
+    const size_t smem = (size_t)SmemRay<SPP>::words(a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
+    static int blocks_per_sm[2] = {0, 0};
+    static int num_sms = 0;
+    const int v = trace ? 1 : 0;
+    if (blocks_per_sm[v] == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        auto kern = trace ? render_kernel<SPP, true> : render_kernel<SPP, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int occ = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem)) != cudaSuccess) return e;
+        blocks_per_sm[v] = occ > 0 ? occ : 1;
+    }
+    const int n_tiles = ((rw + kTileW - 1) / kTileW) * ((rh + kTileH - 1) / kTileH);
+    int grid = num_sms * blocks_per_sm[v];
+    const int need = (n_tiles + kBlockThreads / 32 - 1) / (kBlockThreads / 32);
+    if (grid > need) grid = need;
     if (trace)
         render_kernel<SPP, true><<<grid, kBlockThreads, smem, stream>>>(a);
     else

@@ -10,9 +10,16 @@
 using namespace rto;
 
 namespace {
-struct VecStack {
-    std::vector<uint32_t> v;
-    uint32_t& operator()(int l) { return v[l]; }
+template <int SPP>
+struct HostRay {   // per-ray scratch (shared memory on the GPU: SmemRay in rto_render.cu)
+    std::vector<uint32_t> stk;
+    float d[SPP + 1];
+    uint32_t hl[SPP];
+    float hc[SPP];
+    uint32_t& stack(int l) { return stk[l]; }
+    float& dst(int i) { return d[i]; }
+    uint32_t& hit_leaf(int i) { return hl[i]; }
+    float& hit_cnt(int i) { return hc[i]; }
 };
 
 template <int SPP>
@@ -20,30 +27,29 @@ void run(const uint32_t* nodes, int max_depth, const FrameParams& fp, uint64_t r
          int pix_begin, int pix_end, const float* thresh, uint32_t* steps, int32_t* term, uint32_t* src_bits,
          uint32_t* t_bits, uint64_t* leaf_hash, uint32_t* depth_sum, uint32_t* n_hits, uint32_t* n_loads,
          int32_t* hit_leaf, uint32_t* hit_cnt, int32_t* leaf_seq, int max_seq) {
-    VecStack stack;
-    stack.v.assign(max_depth + 1, 0u);
+    HostRay<SPP> mem;
+    mem.stk.assign(max_depth + 1, 0u);
     for (int idx = pix_begin; idx < pix_end; ++idx) {
         const size_t r = (size_t)(idx - pix_begin);
         RaySetup rs;
         setup_ray(fp, idx % fp.W, idx / fp.W, rs);
-        float dst[SPP + 1];
         if (thresh) {
-            for (int i = 0; i < SPP; ++i) dst[i] = thresh[r * SPP + i];
-            dst[SPP] = FLT_MAX;
+            for (int i = 0; i < SPP; ++i) mem.d[i] = thresh[r * SPP + i];
+            mem.d[SPP] = FLT_MAX;
         } else {
-            sorted_thresholds<SPP>(rng_state, rng_inc, idx, dst);
+            sorted_thresholds<SPP>(rng_state, rng_inc, idx, mem);
         }
-        HitList<SPP> hits;
         WalkOut wo;
         auto sink = [&](uint32_t step, uint32_t leaf) {
             if (leaf_seq && (int)step < max_seq) leaf_seq[r * max_seq + step] = (int32_t)leaf;
         };
-        walk<SPP, true>(nodes, stack, rs, fp.step_size, fp.sigma_thresh, dst, hits, wo, sink);
+        walk<SPP, true>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
         steps[r] = wo.steps; term[r] = wo.term; src_bits[r] = u_bits(wo.src); t_bits[r] = u_bits(wo.t);
-        leaf_hash[r] = wo.hash; depth_sum[r] = wo.depth_sum; n_hits[r] = hits.n; n_loads[r] = wo.n_loads;
+        leaf_hash[r] = wo.hash; depth_sum[r] = wo.depth_sum; n_hits[r] = wo.n_hits; n_loads[r] = wo.n_loads;
         for (int i = 0; i < SPP; ++i) {
-            hit_leaf[r * SPP + i] = (int32_t)hits.leaf[i];
-            hit_cnt[r * SPP + i] = (uint32_t)hits.cnt[i];
+            const bool live = i < (int)wo.n_hits;
+            hit_leaf[r * SPP + i] = live ? (int32_t)mem.hl[i] : -1;
+            hit_cnt[r * SPP + i] = live ? (uint32_t)mem.hc[i] : 0u;
         }
         if (leaf_seq)
             for (int s = (int)wo.steps; s < max_seq; ++s) leaf_seq[r * max_seq + s] = -1;

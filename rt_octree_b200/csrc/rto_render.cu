@@ -12,6 +12,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "rto_internal.h"
 #include "rto_ray.cuh"
 
@@ -19,6 +21,7 @@ namespace rto {
 
 constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
 constexpr int kBlockThreads = 128;         // 4 independent warps per block
+constexpr int kDefaultBlocksPerSM = 6;
 
 // Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
 //   [0, D]            ancestor stack (D = tree max depth)
@@ -190,27 +193,42 @@ __global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 10 : 4)
     }
 }
 
+// Resident blocks per SM of the persistent kernel.  More warps raise issue utilisation but every warp then advances
+// more slowly, and the frame time is bounded below by the LONGEST ray's serial chain, so the optimum
+// is well below the occupancy limit.  RTO_RENDER_BLOCKS_PER_SM overrides the default for tuning.
+static int tuned_blocks_per_sm(int occ_limit) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("RTO_RENDER_BLOCKS_PER_SM");
+        env = e ? atoi(e) : 0;
+    }
+    int want = env > 0 ? env : kDefaultBlocksPerSM;
+    return want < occ_limit ? want : occ_limit;
+}
+
 template <int SPP>
 static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stream) {
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
     const size_t smem = (size_t)SmemRay<SPP>::words(a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
-    static int blocks_per_sm[2] = {0, 0};
+    static size_t smem_set[2] = {0, 0};
+    static int occ_limit[2] = {0, 0};
     static int num_sms = 0;
     const int v = trace ? 1 : 0;
-    if (blocks_per_sm[v] == 0) {
+    auto kern = trace ? render_kernel<SPP, true> : render_kernel<SPP, false>;
+    if (smem > smem_set[v] || occ_limit[v] == 0) {   // first launch, or a deeper tree than any seen before
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        auto kern = trace ? render_kernel<SPP, true> : render_kernel<SPP, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int occ = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem)) != cudaSuccess) return e;
-        blocks_per_sm[v] = occ > 0 ? occ : 1;
+        occ_limit[v] = occ > 0 ? occ : 1;
+        smem_set[v] = smem;
     }
     const int n_tiles = ((rw + kTileW - 1) / kTileW) * ((rh + kTileH - 1) / kTileH);
-    int grid = num_sms * blocks_per_sm[v];
+    int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
     const int need = (n_tiles + kBlockThreads / 32 - 1) / (kBlockThreads / 32);
     if (grid > need) grid = need;
     if (trace)

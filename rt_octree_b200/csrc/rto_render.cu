@@ -21,7 +21,7 @@ namespace rto {
 
 constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
 constexpr int kBlockThreads = 128;         // 4 independent warps per block
-constexpr int kDefaultBlocksPerSM = 6;
+constexpr int kDefaultBlocksPerSM = 6;      // tuned on B200 (tools/sweep_blocks.sh)
 
 // Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
 //   [0, D]            ancestor stack (D = tree max depth)
@@ -38,28 +38,56 @@ struct SmemRay {
     static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1; }
 };
 
-// Persistent kernel: every warp pulls 8x4 pixel tiles from a global counter until the frame (or rectangle) is done,
-// so a warp slot never idles behind a slower sibling warp and the heavy centre rows are handed out first.
+// Persistent kernel.  Work unit = a 16x8 pixel SUPER-TILE (2x2 warp tiles) claimed by a block from a global counter
+// (centre rows first); the block's warps pull the four 8x4 warp tiles of the current super-tile from a shared-memory
+// state word without any barrier, so (a) sibling warps march spatially adjacent rays at the same time and share node
+// sectors in L1, and (b) a warp slot never idles behind a slower sibling: it moves on and claims the next super-tile.
+//   s_state = (super_tile_id << 8) | tiles_taken ; taken == 4 means "next taker refills".
+__device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int lane, int& sid, int& sub) {
+    unsigned r = 0;
+    if (lane == 0) {
+        for (;;) {
+            const unsigned old = atomicAdd(s_state, 1u);
+            const unsigned k = old & 0xffu;
+            if (k < 4u) { r = (old & ~0xffu) | k; break; }
+            if (k == 4u) {   // this warp refills: claim a new super-tile, publish it with sub-tile 0 taken by itself
+                const unsigned nsid = (unsigned)atomicAdd(g_counter, 1);
+                atomicExch(s_state, (nsid << 8) | 1u);
+                r = nsid << 8;
+                break;
+            }
+            while ((*reinterpret_cast<volatile unsigned*>(s_state) & 0xffu) > 4u) __nanosleep(32);   // refill in flight
+        }
+    }
+    r = __shfl_sync(0xffffffffu, r, 0);
+    sid = (int)(r >> 8);
+    sub = (int)(r & 0xffu);
+    return true;
+}
+
 template <int SPP, bool TRACE>
-__global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 10 : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 8 : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
     extern __shared__ uint32_t ray_smem[];
+    __shared__ unsigned s_state;
     const int lane = threadIdx.x & 31;
     const FrameParams& fp = a.fp;
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
-    const int tiles_x = (rw + kTileW - 1) / kTileW, tiles_y = (rh + kTileH - 1) / kTileH;
-    const int n_tiles = tiles_x * tiles_y;
+    const int supers_x = (rw + 2 * kTileW - 1) / (2 * kTileW), supers_y = (rh + 2 * kTileH - 1) / (2 * kTileH);
+    const int n_supers = supers_x * supers_y;
     SmemRay<SPP> mem{ray_smem + threadIdx.x, a.tree.max_depth + 1};
     const uint32_t* __restrict__ nodes = a.tree.nodes;
+    if (threadIdx.x == 0) s_state = ((unsigned)atomicAdd(a.tile_counter, 1) << 8);
+    __syncthreads();
 
     for (;;) {
-        int tile = 0;
-        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-        // centre-first row order: 0 -> mid, 1 -> mid-1, 2 -> mid+1, ...
-        const int tr = tile / tiles_x, tc = tile - tr * tiles_x;
-        const int mid = tiles_y >> 1;
-        const int row = (tr & 1) ? mid - 1 - (tr >> 1) : mid + (tr >> 1);
+        int sid, sub;
+        next_tile(&s_state, a.tile_counter, lane, sid, sub);
+        if (sid >= n_supers) break;
+        // centre-first row order of super-tiles: 0 -> mid, 1 -> mid-1, 2 -> mid+1, ...
+        const int sr = sid / supers_x, sc = sid - sr * supers_x;
+        const int mid = supers_y >> 1;
+        const int srow = (sr & 1) ? mid - 1 - (sr >> 1) : mid + (sr >> 1);
+        const int tc = sc * 2 + (sub & 1), row = srow * 2 + (sub >> 1);
         const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
         const int iy = a.y0 + row * kTileH + (lane / kTileW);
         if (ix < a.x1 && iy < a.y1) {
@@ -227,9 +255,9 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         occ_limit[v] = occ > 0 ? occ : 1;
         smem_set[v] = smem;
     }
-    const int n_tiles = ((rw + kTileW - 1) / kTileW) * ((rh + kTileH - 1) / kTileH);
+    const int n_supers = ((rw + 2 * kTileW - 1) / (2 * kTileW)) * ((rh + 2 * kTileH - 1) / (2 * kTileH));
     int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
-    const int need = (n_tiles + kBlockThreads / 32 - 1) / (kBlockThreads / 32);
+    const int need = n_supers;
     if (grid > need) grid = need;
     if (trace)
         render_kernel<SPP, true><<<grid, kBlockThreads, smem, stream>>>(a);

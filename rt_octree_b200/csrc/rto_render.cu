@@ -21,7 +21,7 @@ namespace rto {
 
 constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
 constexpr int kBlockThreads = 128;         // 4 independent warps per block
-constexpr int kDefaultBlocksPerSM = 6;      // tuned on B200 (tools/sweep_blocks.sh)
+constexpr int kDefaultBlocksPerSM = 8;      // tuned on B200 (tools/sweep_blocks.sh: 4:0.66 5:0.60 6:0.56 8:0.52 ms)
 
 // Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
 //   [0, D]            ancestor stack (D = tree max depth)

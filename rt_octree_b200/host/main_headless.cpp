@@ -1,0 +1,516 @@
+// volrend_headless (B200-native) — drop-in for the reference's headless driver, renderer/main_headless.cpp:192-552.
+//
+//   volrend_headless <tree.npz> <poses> [--options opt.json] [--ts_module weights] [--dataset {blender,tt,llff}]
+//                    [-o dir] [--write_buffer] [--gpu id] [-w -h --fx --fy --bg -s -e -a --scale --max_imgs -r -i --draw]
+//
+// Same flags (opts.cpp:7-31 + main_headless.cpp:202-223), same pose loaders (:255-370), camera conventions (:372-390),
+// 100-frame warm-up protocol (:469-479), per-pose rng.advance() (:506), `buf_<basename>.bin` layout (:512-523) and timer
+// report (render_context.hpp:190-206).  Additions (all optional): --num_gpus N shards the poses over N GPUs (one host
+// thread + one replica of the tree per GPU, no communication); --warmup K; --write_float also dumps the final float4
+// image as `img_<basename>.bin`; --dry_run parses every input and prints a JSON summary without touching a GPU.
+// Differences, on purpose: the tt pose directory is read in sorted order (the reference iterates it unsorted, :282);
+// PNGs are written with zlib directly (the reference needs libpng).
+#include <zlib.h>
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "volrend_b200.hpp"
+
+namespace fs = std::filesystem;
+using namespace volrend;
+
+namespace {
+
+struct Mat43 { float m[12]; };   // column-major 4x3 (glm::mat4x3): m[c*3+r]
+
+// --------------------------------------------------------------------------------------------- CLI parsing
+struct Args {
+    std::map<std::string, std::string> kv;
+    std::vector<std::string> positional;
+    bool has(const std::string& k) const { return kv.count(k) > 0; }
+    std::string str(const std::string& k, const std::string& d = "") const { auto it = kv.find(k); return it == kv.end() ? d : it->second; }
+    int i(const std::string& k, int d) const { return has(k) ? atoi(kv.at(k).c_str()) : d; }
+    float f(const std::string& k, float d) const { return has(k) ? (float)atof(kv.at(k).c_str()) : d; }
+};
+
+Args parse_args(int argc, char** argv) {
+    static const std::map<std::string, std::string> shorts = {{"w", "width"}, {"h", "height"}, {"s", "step_size"}, {"e", "stop_thresh"},
+                                                              {"a", "sigma_thresh"}, {"o", "write_images"}, {"i", "intrin"}, {"r", "reverse_yz"}};
+    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float"};
+    Args a;
+    for (int k = 1; k < argc; ++k) {
+        std::string t = argv[k];
+        if (t.size() >= 2 && t[0] == '-' && !(std::isdigit((unsigned char)t[1]) || t[1] == '.')) {
+            std::string key = t.substr(t[1] == '-' ? 2 : 1), val;
+            const size_t eq = key.find('=');
+            bool has_val = false;
+            if (eq != std::string::npos) { val = key.substr(eq + 1); key = key.substr(0, eq); has_val = true; }
+            if (shorts.count(key)) key = shorts.at(key);
+            if (flags.count(key)) { a.kv[key] = has_val ? val : "1"; continue; }
+            if (!has_val) {
+                if (k + 1 >= argc) { fprintf(stderr, "Option '%s' is missing an argument\n", t.c_str()); std::exit(1); }
+                val = argv[++k];
+            }
+            a.kv[key] = val;
+        } else {
+            a.positional.push_back(t);
+        }
+    }
+    return a;
+}
+
+void print_help() {
+    puts("Headless PlenOctree volume rendering, B200-native RT-Octree path\n"
+         "Usage:\n  volrend_headless [OPTION...] npz_file [c2w_txt_4x4...]\n\n"
+         "      --file arg          npz file storing octree data\n"
+         "      --gpu arg           CUDA device id (default: -1)\n"
+         "  -w, --width arg         image width (default: 800)\n"
+         "  -h, --height arg        image height (default: 800)\n"
+         "      --fx arg            focal length in x direction; -1 = 1111 or default for NDC (default: -1.0)\n"
+         "      --fy arg            focal length in y direction; -1 = use fx (default: -1.0)\n"
+         "      --bg arg            background brightness 0-1 (default: 1.0)\n"
+         "  -s, --step_size arg     step size epsilon added to computed cube size (default: 1e-4)\n"
+         "  -e, --stop_thresh arg   early stopping threshold (on remaining intensity) (default: 1e-2)\n"
+         "  -a, --sigma_thresh arg  sigma threshold (skip cells with < sigma) (default: 1e-2)\n"
+         "      --help              Print this help message\n"
+         "  -o, --write_images arg  output directory of images; if empty, DOES NOT save (for timing only)\n"
+         "  -i, --intrin arg        intrinsics matrix 4x4 (accepted, unused - as in the reference)\n"
+         "  -r, --reverse_yz        use OpenCV camera space convention instead of NeRF\n"
+         "      --scale arg         scaling to apply to image (default: 1)\n"
+         "      --max_imgs arg      max images to render, default no limit (default: 0)\n"
+         "      --options arg       render options json\n"
+         "      --dataset arg       dataset type: blender | tt | llff (default: blender)\n"
+         "      --ts_module arg     GuidanceNet weights (npz export of the reference's ts_*.ts)\n"
+         "      --write_buffer      save auxiliary buffers (buf_<name>.bin). Invalid if output directory is not given.\n"
+         "      --num_gpus arg      shard the poses over this many GPUs (default: 1)\n"
+         "      --warmup arg        warm-up frames on pose 0 (default: 100)\n"
+         "      --write_float       also save the final float4 image as img_<name>.bin\n"
+         "      --dry_run           parse all inputs, print a JSON summary, do not touch the GPU");
+}
+
+// ------------------------------------------------------------------------------------------- small vector math
+struct V3 { float x, y, z; };
+V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+V3 cross(V3 a, V3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+V3 normalize3(V3 v) {   // main_headless.cpp:102-106
+    const float n = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    return {v.x / n, v.y / n, v.z / n};
+}
+V3 col(const Mat43& t, int c) { return {t.m[c * 3], t.m[c * 3 + 1], t.m[c * 3 + 2]}; }
+
+// general 4x4 inverse (column-major), cofactor expansion in float like glm::inverse
+void inverse4(const float* a, float* inv) {
+    float t[16];
+    t[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
+    t[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
+    t[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
+    t[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
+    t[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
+    t[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
+    t[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
+    t[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
+    t[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
+    t[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
+    t[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
+    t[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
+    t[3] = -a[1] * a[6] * a[11] + a[1] * a[7] * a[10] + a[5] * a[2] * a[11] - a[5] * a[3] * a[10] - a[9] * a[2] * a[7] + a[9] * a[3] * a[6];
+    t[7] = a[0] * a[6] * a[11] - a[0] * a[7] * a[10] - a[4] * a[2] * a[11] + a[4] * a[3] * a[10] + a[8] * a[2] * a[7] - a[8] * a[3] * a[6];
+    t[11] = -a[0] * a[5] * a[11] + a[0] * a[7] * a[9] + a[4] * a[1] * a[11] - a[4] * a[3] * a[9] - a[8] * a[1] * a[7] + a[8] * a[3] * a[5];
+    t[15] = a[0] * a[5] * a[10] - a[0] * a[6] * a[9] - a[4] * a[1] * a[10] + a[4] * a[2] * a[9] + a[8] * a[1] * a[6] - a[8] * a[2] * a[5];
+    const float det = a[0] * t[0] + a[1] * t[4] + a[2] * t[8] + a[3] * t[12];
+    const float id = 1.0f / det;
+    for (int i = 0; i < 16; ++i) inv[i] = t[i] * id;
+}
+
+// _recenter_poses (main_headless.cpp:152-189): pose <- inverse(poses_avg) * pose
+void recenter_poses(std::vector<Mat43>& trans) {
+    V3 z{0, 0, 0}, up{0, 0, 0}, cen{0, 0, 0};
+    for (const Mat43& t : trans) { z = z + col(t, 2); up = up + col(t, 1); cen = cen + col(t, 3); }
+    const float n = (float)trans.size();
+    z = normalize3(z / n);
+    up = up / n;
+    cen = cen / n;
+    // _viewmatrix(z, up, pos)
+    z = normalize3(z);
+    const V3 x = normalize3(cross(up, z));
+    const V3 y = normalize3(cross(z, x));
+    float c2w[16] = {x.x, x.y, x.z, 0, y.x, y.y, y.z, 0, z.x, z.y, z.z, 0, cen.x, cen.y, cen.z, 1};
+    float inv[16];
+    inverse4(c2w, inv);
+    for (Mat43& p : trans) {
+        float p4[16] = {p.m[0], p.m[1], p.m[2], 0, p.m[3], p.m[4], p.m[5], 0, p.m[6], p.m[7], p.m[8], 0, p.m[9], p.m[10], p.m[11], 1};
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 3; ++r) {
+                float s = 0.f;
+                for (int k = 0; k < 4; ++k) s += inv[k * 4 + r] * p4[c * 4 + k];
+                p.m[c * 3 + r] = s;
+            }
+    }
+}
+
+std::string remove_ext(const std::string& s) {
+    const size_t p = s.rfind('.');
+    return p == std::string::npos ? s : s.substr(0, p);
+}
+
+std::string read_text(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) { fprintf(stderr, "ERROR: '%s' does not exist\n", path.c_str()); std::exit(1); }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// read_transform_matrices (main_headless.cpp:62-91): a file may hold several 4x4 row-major matrices
+int read_transform_matrices(const std::string& path, std::vector<Mat43>& out) {
+    std::ifstream ifs(path);
+    if (!ifs) { fprintf(stderr, "ERROR: '%s' does not exist\n", path.c_str()); std::exit(1); }
+    int cnt = 0;
+    while (ifs) {
+        Mat43 t;
+        float garb;
+        ifs >> t.m[0] >> t.m[3] >> t.m[6] >> t.m[9];
+        if (!ifs) break;
+        ifs >> t.m[1] >> t.m[4] >> t.m[7] >> t.m[10];
+        ifs >> t.m[2] >> t.m[5] >> t.m[8] >> t.m[11];
+        if (ifs) ifs >> garb >> garb >> garb >> garb;
+        ++cnt;
+        out.push_back(t);
+    }
+    return cnt;
+}
+
+// ------------------------------------------------------------------------------------------------- PNG (RGBA8)
+void put32(std::vector<unsigned char>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((unsigned char)(x >> s)); }
+void png_chunk(std::vector<unsigned char>& out, const char* type, const std::vector<unsigned char>& data) {
+    put32(out, (uint32_t)data.size());
+    const size_t start = out.size();
+    out.insert(out.end(), type, type + 4);
+    out.insert(out.end(), data.begin(), data.end());
+    put32(out, (uint32_t)crc32(0L, out.data() + start, (uInt)(out.size() - start)));
+}
+bool write_png_file(const std::string& path, const uint8_t* rgba, int w, int h) {   // src/imwrite.cpp:14-78 (RGBA8, compression 0)
+    std::vector<unsigned char> raw((size_t)h * (w * 4 + 1));
+    for (int y = 0; y < h; ++y) {
+        raw[(size_t)y * (w * 4 + 1)] = 0;
+        memcpy(&raw[(size_t)y * (w * 4 + 1) + 1], rgba + (size_t)y * w * 4, (size_t)w * 4);
+    }
+    uLongf clen = compressBound((uLong)raw.size());
+    std::vector<unsigned char> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 1) != Z_OK) return false;
+    comp.resize(clen);
+    std::vector<unsigned char> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<unsigned char> ihdr;
+    put32(ihdr, (uint32_t)w); put32(ihdr, (uint32_t)h);
+    ihdr.insert(ihdr.end(), {8, 6, 0, 0, 0});
+    png_chunk(out, "IHDR", ihdr);
+    png_chunk(out, "IDAT", comp);
+    png_chunk(out, "IEND", {});
+    std::ofstream f(path, std::ios::binary);
+    f.write(reinterpret_cast<const char*>(out.data()), (std::streamsize)out.size());
+    return bool(f);
+}
+
+uint64_t fnv64(const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+
+struct Job {
+    std::string tree_path, out_dir, ts_module;
+    std::vector<Mat43> trans;
+    std::vector<std::string> basenames;
+    RenderOptions options;
+    int width, height;
+    float fx, fy;
+    bool llff, write_buffer, write_float;
+    int warmup;
+};
+
+// one GPU: frames [begin, end) of the job; ms[3]/frames receive this shard's timer sums
+void run_shard(const Job& job, int device, size_t begin, size_t end, float* ms, int* frames, bool verbose) {
+    if (device >= 0) rto_check(rto_set_device(device), "cudaSetDevice");
+    N3Tree tree(job.tree_path);
+    if (!tree.is_data_loaded()) std::exit(1);
+    if (job.llff) {   // main_headless.cpp:400-405
+        tree.use_ndc = true;
+        tree.ndc_width = (float)job.width;
+        tree.ndc_height = (float)job.height;
+        tree.ndc_focal = job.fx;
+    }
+    tree.sync_ndc();
+    Camera camera(job.width, job.height, job.fx, job.fy);
+    std::vector<float> buf;
+    if (job.out_dir.size()) buf.resize((size_t)RenderContext::CHANNELS * job.width * job.height);
+    void* stream = nullptr;   // the reference creates a blocking stream (cudaStreamDefault); the legacy stream is equivalent here
+    RenderContext ctx;
+    ctx.offscreen = true;
+    ctx.update(job.width, job.height);
+    // created unconditionally, like the reference (main_headless.cpp:455-456): an empty --ts_module throws
+    std::unique_ptr<Denoiser> denoiser = std::make_unique<Denoiser>(job.ts_module);
+    const RenderOptions& options = job.options;
+
+    memcpy(camera.transform, job.trans[0].m, sizeof camera.transform);
+    camera._update(false);
+    for (int i = 0; i < job.warmup; ++i) {   // warm up, main_headless.cpp:469-479
+        launch_renderer(tree, camera, options, ctx, stream, true);
+        if (options.denoise) denoiser->denoise(camera, ctx, stream);
+        ctx.rng.advance();
+    }
+    // frame-sharded: the rng is a pure function of the global frame index, identical to the single-GPU sequence
+    rto_check(rto_context_rng_set_frame(ctx.handle, job.warmup, (int64_t)begin), "rng");
+    ctx.timer().reset(stream);
+    for (size_t i = begin; i < end; ++i) {
+        memcpy(camera.transform, job.trans[i].m, sizeof camera.transform);
+        camera._update(false);
+        ctx.timer().render_start();
+        launch_renderer(tree, camera, options, ctx, stream, true);
+        ctx.timer().render_stop();
+        if (options.denoise) denoiser->denoise(camera, ctx, stream);
+        ctx.timer().record(options.denoise);
+        ctx.rng.advance();
+        if (!job.out_dir.size()) continue;
+        if (job.write_buffer) {   // main_headless.cpp:512-523
+            rto_check(rto_context_read_aux(ctx.handle, buf.data(), stream), "read aux");
+            rto_check(rto_synchronize(stream), "sync");
+            std::ofstream out(job.out_dir + "/buf_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
+            out.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)(buf.size() * sizeof(float)));
+        } else {                  // main_headless.cpp:524-541
+            rto_check(rto_context_read_image(ctx.handle, buf.data(), stream), "read image");
+            rto_check(rto_synchronize(stream), "sync");
+            std::vector<uint8_t> u8((size_t)4 * job.width * job.height);
+            for (size_t j = 0; j < u8.size(); ++j) u8[j] = (uint8_t)(buf[j] * 255);   // truncation, no clamp — as the reference
+            write_png_file(job.out_dir + "/" + job.basenames[i] + ".png", u8.data(), job.width, job.height);
+        }
+        if (job.write_float) {
+            std::vector<float> img((size_t)4 * job.width * job.height);
+            rto_check(rto_context_read_image(ctx.handle, img.data(), stream), "read image");
+            rto_check(rto_synchronize(stream), "sync");
+            std::ofstream out(job.out_dir + "/img_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
+            out.write(reinterpret_cast<const char*>(img.data()), (std::streamsize)(img.size() * sizeof(float)));
+        }
+    }
+    rto_check(rto_synchronize(stream), "sync");
+    rto_check(rto_timer_report(ctx.handle, ms, frames), "timer");
+    if (verbose) ctx.timer().report();
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    Args args = parse_args(argc, argv);
+    if (args.has("help")) { print_help(); return 0; }
+    std::string tree_path = args.str("file");
+    std::vector<std::string> rest = args.positional;
+    if (tree_path.empty() && !rest.empty()) { tree_path = rest[0]; rest.erase(rest.begin()); }
+    if (tree_path.empty() || rest.size() != 1) {
+        fprintf(stderr, "usage: volrend_headless <tree.npz> <poses> [options]   (--help for the list)\n");
+        return 1;
+    }
+    const fs::path poses_path = rest[0];
+    const int device_id = args.i("gpu", -1);
+
+    int width = args.i("width", 800), height = args.i("height", 800);
+    float fx = args.f("fx", -1.f);
+    if (fx < 0) fx = 1111.11f;
+    float fy = args.f("fy", -1.f);
+    if (fy < 0) fy = fx;
+
+    Job job;
+    std::vector<Mat43>& trans = job.trans;
+    std::vector<std::string>& basenames = job.basenames;
+    const std::string dataset_type = args.str("dataset", "blender");
+    if (dataset_type == "blender") {   // main_headless.cpp:255-272
+        const rtohost::Json poses = rtohost::Json::parse(read_text(poses_path.string()));
+        const float camera_angle_x = (float)poses.at("camera_angle_x").as_number();
+        fx = fy = 0.5f * width / tanf(0.5f * camera_angle_x);
+        const rtohost::Json& frames = poses.at("frames");
+        for (size_t i = 0; i < frames.size(); ++i) {
+            const rtohost::Json& m = frames[i].at("transform_matrix");
+            Mat43 t;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 4; ++c) t.m[c * 3 + r] = (float)m[r][c].as_number();
+            trans.push_back(t);
+            basenames.push_back("r_" + std::to_string(i));
+        }
+    } else if (dataset_type == "tt") {   // main_headless.cpp:273-297
+        width = 1920;
+        height = 1080;
+        {
+            std::ifstream ifs((poses_path / ".." / "intrinsics.txt").string());
+            if (!ifs) { fprintf(stderr, "ERROR: intrin '%s' does not exist\n", (poses_path / ".." / "intrinsics.txt").string().c_str()); return 1; }
+            float g;
+            ifs >> fx >> g >> g >> g;
+            ifs >> g >> fy;
+        }
+        std::vector<fs::path> files;
+        for (const auto& e : fs::directory_iterator(poses_path)) files.push_back(e.path());
+        std::sort(files.begin(), files.end());
+        for (const fs::path& p : files) {
+            const int cnt = read_transform_matrices(p.string(), trans);
+            const std::string fname = remove_ext(p.filename().string());
+            if (cnt == 1) basenames.push_back(fname);
+            else
+                for (int i = 0; i < cnt; ++i) {
+                    std::string tmp = std::to_string(i);
+                    while (tmp.size() < 6) tmp = "0" + tmp;
+                    basenames.push_back(fname + "_" + tmp);
+                }
+        }
+    } else if (dataset_type == "llff") {   // main_headless.cpp:298-370
+        const rtohost::NpyArray poses = rtohost::npy_load(poses_path.string());
+        const size_t pose_cnt = poses.shape[0], per = poses.shape[1];
+        auto get = [&](size_t set, size_t idx) -> float {
+            const size_t k = set * per + idx;
+            return poses.word_size == 4 ? poses.data<float>()[k] : (float)poses.data<double>()[k];
+        };
+        constexpr int factor = 4;
+        width = (int)(get(0, 9) / factor);
+        height = (int)(get(0, 4) / factor);
+        fx = fy = get(0, 14) / factor;
+        float bds_min = 1e9f;
+        for (size_t p = 0; p < pose_cnt; ++p) bds_min = std::min(bds_min, get(p, 15));
+        for (size_t p = 0; p < pose_cnt; ++p) {
+            float t[12];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 4; ++j) t[j * 3 + i] = get(p, (size_t)i * 5 + j);
+            Mat43 r;   // temp * cam_trans: col0 <- col1, col1 <- -col0
+            for (int i = 0; i < 3; ++i) { r.m[i] = t[3 + i]; r.m[3 + i] = -t[i]; r.m[6 + i] = t[6 + i]; r.m[9 + i] = t[9 + i]; }
+            const float scale = 1.0f / (bds_min * 0.75f);
+            for (int i = 0; i < 3; ++i) r.m[9 + i] *= scale;
+            trans.push_back(r);
+        }
+        std::string images_dirname = "images";
+        if (factor > 1) images_dirname += "_" + std::to_string(factor);
+        const fs::path images_path = poses_path.parent_path() / images_dirname;
+        for (const auto& e : fs::directory_iterator(images_path)) basenames.push_back(remove_ext(e.path().filename().string()));
+        std::sort(basenames.begin(), basenames.end());
+    } else {
+        fprintf(stderr, "ERROR: unknown dataset type '%s'\n", dataset_type.c_str());
+        return 1;
+    }
+
+    // camera convention (main_headless.cpp:372-390)
+    if (dataset_type == "tt" || args.has("reverse_yz")) {
+        puts("INFO: Use OpenCV camera convention\n");
+        for (Mat43& t : trans)
+            for (int i = 3; i < 9; ++i) t.m[i] = -t.m[i];   // * diag(1,-1,-1,1): flip the up and back columns
+    } else if (dataset_type == "llff") {
+        puts("INFO: Use LLFF camera convention\n");
+        recenter_poses(trans);
+    } else {
+        puts("INFO: Use NeRF camera convention\n");
+    }
+    if (trans.empty()) { fputs("WARNING: No camera poses specified, quitting\n", stderr); return 1; }
+    while (basenames.size() < trans.size()) basenames.push_back("frame_" + std::to_string(basenames.size()));
+
+    {   // --scale (main_headless.cpp:407-418)
+        const float scale = args.f("scale", 1.f);
+        if (scale != 1.f) {
+            const int ow = width, oh = height;
+            width = (int)(width * scale);
+            height = (int)(height * scale);
+            fx *= (float)width / ow;
+            fy *= (float)height / oh;
+        }
+    }
+    {
+        const int max_imgs = args.i("max_imgs", 0);
+        if (max_imgs > 0 && trans.size() > (size_t)max_imgs) { trans.resize(max_imgs); basenames.resize(max_imgs); }
+    }
+
+    job.tree_path = tree_path;
+    job.out_dir = args.str("write_images");
+    job.ts_module = args.str("ts_module");
+    job.width = width; job.height = height; job.fx = fx; job.fy = fy;
+    job.llff = dataset_type == "llff";
+    job.write_buffer = args.has("write_buffer");
+    job.write_float = args.has("write_float");
+    job.warmup = args.i("warmup", 100);
+    if (job.out_dir.size()) fs::create_directories(job.out_dir);
+
+    // render options (main_headless.cpp:459-467; opts.cpp:44-66)
+    const std::string options_path = args.str("options");
+    if (!options_path.empty()) {
+        job.options = RenderOptions::from_json(rtohost::Json::parse(read_text(options_path)));
+    } else {
+        job.options.background_brightness = args.f("bg", 1.0f);
+        job.options.step_size = args.f("step_size", 1e-4f);
+        job.options.stop_thresh = args.f("stop_thresh", 1e-2f);
+        job.options.sigma_thresh = args.f("sigma_thresh", 1e-2f);
+    }
+
+    if (args.has("dry_run")) {
+        rtohost::npz_t z = rtohost::npz_load(tree_path);
+        const rtohost::NpyArray& ch = z.at("child");
+        printf("{\"poses\": %zu, \"width\": %d, \"height\": %d, \"fx\": %.9g, \"fy\": %.9g, \"spp\": %d, \"denoise\": %s, "
+               "\"step_size\": %.9g, \"sigma_thresh\": %.9g, \"background\": %.9g, \"capacity\": %zu, \"data_dim\": %d, "
+               "\"data_format\": \"%s\", \"child_fnv\": \"%016llx\", \"data_fnv\": \"%016llx\", \"pose0\": [",
+               trans.size(), width, height, fx, fy, job.options.spp, job.options.denoise ? "true" : "false", job.options.step_size,
+               job.options.sigma_thresh, job.options.background_brightness, ch.shape[0], (int)z.at("data_dim").scalar_as_double(),
+               z.count("data_format") ? z.at("data_format").as_string().c_str() : "", (unsigned long long)fnv64(ch.bytes.data(), ch.bytes.size()),
+               z.count("data") ? (unsigned long long)fnv64(z.at("data").bytes.data(), z.at("data").bytes.size()) : 0ull);
+        for (int i = 0; i < 12; ++i) printf("%s%.9g", i ? ", " : "", trans[0].m[i]);
+        printf("], \"pose_last\": [");
+        for (int i = 0; i < 12; ++i) printf("%s%.9g", i ? ", " : "", trans.back().m[i]);
+        printf("], \"basename0\": \"%s\"}\n", basenames[0].c_str());
+        return 0;
+    }
+
+    int num_gpus = args.i("num_gpus", 1);
+    if (num_gpus < 1) num_gpus = 1;
+    try {
+        if (num_gpus == 1) {
+            float ms[3];
+            int n = 0;
+            run_shard(job, device_id, 0, trans.size(), ms, &n, true);
+        } else {
+            // frame sharding: contiguous slices of the pose list, one host thread and one replica per GPU, no collective
+            std::vector<std::thread> th;
+            std::vector<std::array<float, 3>> ms(num_gpus);
+            std::vector<int> frames(num_gpus, 0);
+            const size_t n = trans.size();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int g = 0; g < num_gpus; ++g) {
+                const size_t b = n * g / num_gpus, e = n * (g + 1) / num_gpus;
+                th.emplace_back([&, g, b, e]() { run_shard(job, g, b, e, ms[g].data(), &frames[g], false); });
+            }
+            for (auto& t : th) t.join();
+            const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            float agg[3] = {0, 0, 0};
+            int tot = 0;
+            for (int g = 0; g < num_gpus; ++g) {
+                for (int k = 0; k < 3; ++k) agg[k] += ms[g][k] * frames[g];
+                tot += frames[g];
+            }
+            float all = 0.f;
+            const char* names[3] = {"render", "torch: ", "filter"};
+            for (int k = 0; k < 3; ++k) { printf("%s: %.10f ms per frame\n", k == 1 ? "torch" : names[k], agg[k] / tot); all += agg[k] / tot; }
+            printf("all:    %.10f ms per frame\n", all);
+            printf("FPS:    %.10f   (per GPU; %d GPUs, %d frames, wall %.3f s incl. load + warm-up)\n", 1000.f / all, num_gpus, tot, wall);
+            printf("aggregate FPS: %.10f\n", num_gpus * 1000.f / all);
+        }
+    } catch (const std::exception& e) {
+        fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", e.what());
+        return 134;
+    }
+    return 0;
+}

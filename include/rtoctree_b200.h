@@ -70,6 +70,8 @@ typedef struct rto_tree_info {
     int64_t n_leaves;
     int64_t node_bytes, payload_bytes; /* HBM footprint of the SoA layout */
     int payload_stride_halfs;
+    int grid_level;          /* K of the sparse brick grid used by the marching loop (0 = none) */
+    int64_t n_bricks, grid_bytes;
     float offset[3], scale[3];
     float ndc_width, ndc_height, ndc_focal;
 } rto_tree_info;

@@ -39,7 +39,8 @@ class RenderOptionsPOD(C.Structure):
 class TreeInfoPOD(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("N", C.c_int), ("data_dim", C.c_int), ("format", C.c_int),
                 ("basis_dim", C.c_int), ("max_depth", C.c_int), ("n_leaves", C.c_int64), ("node_bytes", C.c_int64),
-                ("payload_bytes", C.c_int64), ("payload_stride_halfs", C.c_int), ("offset", C.c_float * 3),
+                ("payload_bytes", C.c_int64), ("payload_stride_halfs", C.c_int), ("grid_level", C.c_int), ("n_bricks", C.c_int64),
+                ("grid_bytes", C.c_int64), ("offset", C.c_float * 3),
                 ("scale", C.c_float * 3), ("ndc_width", C.c_float), ("ndc_height", C.c_float), ("ndc_focal", C.c_float)]
 
 

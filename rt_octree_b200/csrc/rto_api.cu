@@ -5,11 +5,14 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/rtoctree_b200.h"
+#include "rto_grid_host.h"
 #include "rto_internal.h"
 
 namespace rto {
@@ -28,6 +31,10 @@ cudaError_t denoise_tc_set_debug(float* p);
 struct rto_tree {
     uint32_t* nodes = nullptr;
     __half* payload = nullptr;
+    uint32_t* grid_top = nullptr;      // sparse brick grid (rto_ray.cuh GridDev), optional
+    uint32_t* grid_bricks = nullptr;
+    int grid_K = 0;
+    int64_t n_bricks = 0;
     rto_tree_info info{};
 };
 
@@ -204,12 +211,35 @@ int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, 
         delete t;
         return fail(RTO_ERR_INVALID, "malformed tree: child offset out of range");
     }
+    {   // sparse brick grid for the marching loop (skipped for very shallow / very deep trees or RTO_DISABLE_GRID=1)
+        const char* off = getenv("RTO_DISABLE_GRID");
+        std::vector<uint32_t> top, bricks;
+        int K = 0;
+        if (!(off && off[0] == '1') &&
+            rto::build_grid_host(child, static_cast<const uint16_t*>(data_f16), data_dim, capacity, max_depth, top, bricks, K)) {
+            cudaError_t ge = cudaMalloc(&t->grid_top, top.size() * sizeof(uint32_t));
+            if (ge == cudaSuccess) ge = cudaMalloc(&t->grid_bricks, (bricks.empty() ? 512 : bricks.size()) * sizeof(uint32_t));
+            if (ge == cudaSuccess) ge = cudaMemcpy(t->grid_top, top.data(), top.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+            if (ge == cudaSuccess && !bricks.empty())
+                ge = cudaMemcpy(t->grid_bricks, bricks.data(), bricks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+            if (ge != cudaSuccess) {
+                cudaFree(t->nodes); cudaFree(t->payload); cudaFree(t->grid_top); cudaFree(t->grid_bricks);
+                delete t;
+                return fail(ge == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "grid upload: %s", cudaGetErrorString(ge));
+            }
+            t->grid_K = K;
+            t->n_bricks = (int64_t)(bricks.size() / 512);
+        }
+    }
     rto_tree_info& I = t->info;
     I.capacity = capacity; I.N = N; I.data_dim = data_dim; I.format = format; I.basis_dim = basis_dim;
     I.max_depth = max_depth; I.n_leaves = (int64_t)n_leaves;
     I.node_bytes = n_entries * (int64_t)sizeof(uint32_t);
     I.payload_bytes = n_entries * (int64_t)stride * (int64_t)sizeof(__half);
     I.payload_stride_halfs = stride;
+    I.grid_level = t->grid_K;
+    I.n_bricks = t->n_bricks;
+    I.grid_bytes = t->grid_K ? (int64_t)((((size_t)1 << (3 * t->grid_K)) + (size_t)t->n_bricks * 512) * sizeof(uint32_t)) : 0;
     for (int i = 0; i < 3; ++i) { I.offset[i] = offset[i]; I.scale[i] = scale[i]; }
     I.ndc_width = -1.f; I.ndc_height = 0.f; I.ndc_focal = 0.f;
     *out = t;
@@ -230,6 +260,8 @@ void rto_tree_destroy(rto_tree* t) {
     if (!t) return;
     cudaFree(t->nodes);
     cudaFree(t->payload);
+    cudaFree(t->grid_top);
+    cudaFree(t->grid_bricks);
     delete t;
 }
 
@@ -324,7 +356,8 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     fp.ndc_width = t->info.ndc_width; fp.ndc_height = t->info.ndc_height; fp.ndc_focal = t->info.ndc_focal;
     fp.step_size = opt->step_size; fp.sigma_thresh = opt->sigma_thresh; fp.background = opt->background_brightness;
     fp.W = c->W; fp.H = c->H;
-    a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth};
+    a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth,
+                          rto::GridDev{t->grid_top, t->grid_bricks, t->grid_K}};
     a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;

@@ -1,0 +1,62 @@
+// rto_grid_host.h — host-side builder of the sparse brick grid (plain C++, shared by rto_api.cu and the CPU test harness).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "rto_ray.cuh"
+
+namespace rto {
+
+// Sparse brick grid (rto_ray.cuh GridDev), built on the host from the original tree.npz arrays at load time.
+// Returns false (no grid) when the depth is outside the supported range.
+inline bool build_grid_host(const int32_t* child, const uint16_t* data, int data_dim, int64_t capacity, int max_depth,
+                     std::vector<uint32_t>& top, std::vector<uint32_t>& bricks, int& K) {
+    (void)capacity;
+    const int D = max_depth;
+    if (D < 4 || D > 11) return false;   // K = D-3 in [1, 8]
+    K = D - 3;
+    const size_t S = (size_t)1 << K;
+    top.assign(S * S * S, 0u);
+    bricks.clear();
+    struct Item { int64_t node; int l; uint32_t x, y, z; int64_t brick; };
+    std::vector<Item> stack;
+    stack.push_back({0, 0, 0u, 0u, 0u, -1});
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        for (int o = 0; o < 8; ++o) {
+            const uint32_t cx = it.x * 2 + ((o >> 2) & 1), cy = it.y * 2 + ((o >> 1) & 1), cz = it.z * 2 + (o & 1);
+            const int d = it.l + 1;   // depth (look-ups) of a leaf child / level of an internal child
+            const int64_t e = it.node * 8 + o;
+            const int32_t skip = child[e];
+            if (skip == 0) {
+                const uint32_t word = RTO_LEAF_FLAG | ((uint32_t)d << 16) | data[e * data_dim + data_dim - 1];
+                if (d <= K) {
+                    const uint32_t s = 1u << (K - d);
+                    for (uint32_t a = 0; a < s; ++a)
+                        for (uint32_t b = 0; b < s; ++b)
+                            for (uint32_t c = 0; c < s; ++c)
+                                top[(((size_t)(cx * s + a) << K) | (cy * s + b)) << K | (cz * s + c)] = word;
+                } else {
+                    const uint32_t s = 1u << (D - d);
+                    const uint32_t lx = (cx * s) & 7u, ly = (cy * s) & 7u, lz = (cz * s) & 7u;
+                    uint32_t* br = bricks.data() + (size_t)it.brick * 512;
+                    for (uint32_t a = 0; a < s; ++a)
+                        for (uint32_t b = 0; b < s; ++b)
+                            for (uint32_t c = 0; c < s; ++c) br[((lx + a) << 6) | ((ly + b) << 3) | (lz + c)] = word;
+                }
+            } else {
+                int64_t brick = it.brick;
+                if (d == K) {
+                    brick = (int64_t)(bricks.size() / 512);
+                    bricks.resize(bricks.size() + 512, 0u);
+                    top[(((size_t)cx << K) | cy) << K | cz] = (uint32_t)brick;
+                }
+                stack.push_back({it.node + skip, d, cx, cy, cz, brick});
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace rto

@@ -16,6 +16,7 @@ struct TreeDev {
     int sh_stride;          // halfs per leaf, multiple of 8 (27 -> 32 = 64 B for SH9)
     int basis_dim;          // >0: SH with that many coefficients per channel ; <=0: RGBA leaves
     int max_depth;          // max child look-ups to reach a leaf (sizes the per-ray ancestor stack)
+    GridDev grid;           // sparse brick grid (grid.K == 0: none)
 };
 
 struct TraceOut {           // all optional (nullptr); indexed by the FULL-FRAME pixel index

@@ -35,7 +35,7 @@ struct SmemRay {
     __device__ __forceinline__ float& dst(int i) { return reinterpret_cast<float*>(base)[(off_dst + i) * kBlockThreads]; }
     __device__ __forceinline__ uint32_t& hit_leaf(int i) { return base[(off_dst + SPP + 1 + i) * kBlockThreads]; }
     __device__ __forceinline__ float& hit_cnt(int i) { return reinterpret_cast<float*>(base)[(off_dst + 2 * SPP + 1 + i) * kBlockThreads]; }
-    static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1; }
+    static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1; }   // max_depth = -1: no stack
 };
 
 // Persistent kernel.  Work unit = a 16x8 pixel SUPER-TILE (2x2 warp tiles) claimed by a block from a global counter
@@ -65,8 +65,11 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
     return true;
 }
 
-template <int SPP, bool TRACE>
+// GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent; TRACE builds
+// always use the tree walker because they must report the leaf visited at every step.
+template <int SPP, bool TRACE, bool GRID>
 __global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 8 : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
+    static_assert(!(TRACE && GRID), "trace builds use the tree walker");
     extern __shared__ uint32_t ray_smem[];
     __shared__ unsigned s_state;
     const int lane = threadIdx.x & 31;
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 8 : 4))
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     const int supers_x = (rw + 2 * kTileW - 1) / (2 * kTileW), supers_y = (rh + 2 * kTileH - 1) / (2 * kTileH);
     const int n_supers = supers_x * supers_y;
-    SmemRay<SPP> mem{ray_smem + threadIdx.x, a.tree.max_depth + 1};
+    SmemRay<SPP> mem{ray_smem + threadIdx.x, GRID ? 0 : a.tree.max_depth + 1};
     const uint32_t* __restrict__ nodes = a.tree.nodes;
     if (threadIdx.x == 0) s_state = ((unsigned)atomicAdd(a.tile_counter, 1) << 8);
     __syncthreads();
@@ -103,7 +106,10 @@ __global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 8 : 4))
             auto sink = [&](uint32_t step, uint32_t leaf) {
                 if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
             };
-            walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+            if constexpr (GRID)
+                walk_grid<SPP, false>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+            else
+                walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             const uint32_t sh_nums = wo.n_hits;
 
             if (TRACE) {
@@ -238,12 +244,13 @@ template <int SPP>
 static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stream) {
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
-    const size_t smem = (size_t)SmemRay<SPP>::words(a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
-    static size_t smem_set[2] = {0, 0};
-    static int occ_limit[2] = {0, 0};
+    const bool grid_path = !trace && a.tree.grid.K > 0;
+    const int v = trace ? 1 : (grid_path ? 2 : 0);
+    const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
+    static size_t smem_set[3] = {0, 0, 0};
+    static int occ_limit[3] = {0, 0, 0};
     static int num_sms = 0;
-    const int v = trace ? 1 : 0;
-    auto kern = trace ? render_kernel<SPP, true> : render_kernel<SPP, false>;
+    void (*kern)(RenderArgs) = trace ? render_kernel<SPP, true, false> : (grid_path ? render_kernel<SPP, false, true> : render_kernel<SPP, false, false>);
     if (smem > smem_set[v] || occ_limit[v] == 0) {   // first launch, or a deeper tree than any seen before
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
@@ -259,10 +266,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
     int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;
-    if (trace)
-        render_kernel<SPP, true><<<grid, kBlockThreads, smem, stream>>>(a);
-    else
-        render_kernel<SPP, false><<<grid, kBlockThreads, smem, stream>>>(a);
+    kern<<<grid, kBlockThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "rto_grid_host.h"
 #include "rto_internal.h"
 
 namespace rto {
@@ -97,5 +98,6 @@ int tree_max_depth_host(const int32_t* child, int64_t capacity) {
     }
     return depth;
 }
+
 
 }  // namespace rto

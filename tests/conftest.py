@@ -53,15 +53,18 @@ def host_ray_lib():
 
     src = os.path.join(ROOT, "tests", "host_ray_harness.cpp")
     hdr = os.path.join(ROOT, "rt_octree_b200", "csrc", "rto_ray.cuh")
+    hdr2 = os.path.join(ROOT, "rt_octree_b200", "csrc", "rto_grid_host.h")
     so = os.path.join(ROOT, "tests", "_build", "libhost_ray.so")
     os.makedirs(os.path.dirname(so), exist_ok=True)
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-mf16c", "-fPIC", "-shared",
                         src, "-o", so], check=True)
     lib = C.CDLL(so)
     P, I, F, U64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
     lib.host_ray_walk.restype = I
     lib.host_ray_walk.argtypes = [P, I, P, P, P, F, F, F, F, F, F, F, I, I, I, U64, U64, I, I, P] + [P] * 11 + [I]
+    lib.host_ray_set_grid.restype = I
+    lib.host_ray_set_grid.argtypes = [P, P, I, C.c_int64, I, P]
     return lib
 
 

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "../rt_octree_b200/csrc/rto_grid_host.h"
 #include "../rt_octree_b200/csrc/rto_ray.cuh"
 
 using namespace rto;
@@ -23,7 +24,7 @@ struct HostRay {   // per-ray scratch (shared memory on the GPU: SmemRay in rto_
 };
 
 template <int SPP>
-void run(const uint32_t* nodes, int max_depth, const FrameParams& fp, uint64_t rng_state, uint64_t rng_inc,
+void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameParams& fp, uint64_t rng_state, uint64_t rng_inc,
          int pix_begin, int pix_end, const float* thresh, uint32_t* steps, int32_t* term, uint32_t* src_bits,
          uint32_t* t_bits, uint64_t* leaf_hash, uint32_t* depth_sum, uint32_t* n_hits, uint32_t* n_loads,
          int32_t* hit_leaf, uint32_t* hit_cnt, int32_t* leaf_seq, int max_seq) {
@@ -43,7 +44,10 @@ void run(const uint32_t* nodes, int max_depth, const FrameParams& fp, uint64_t r
         auto sink = [&](uint32_t step, uint32_t leaf) {
             if (leaf_seq && (int)step < max_seq) leaf_seq[r * max_seq + step] = (int32_t)leaf;
         };
-        walk<SPP, true>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+        if (grid)
+            walk_grid<SPP, true>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+        else
+            walk<SPP, true>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
         steps[r] = wo.steps; term[r] = wo.term; src_bits[r] = u_bits(wo.src); t_bits[r] = u_bits(wo.t);
         leaf_hash[r] = wo.hash; depth_sum[r] = wo.depth_sum; n_hits[r] = wo.n_hits; n_loads[r] = wo.n_loads;
         for (int i = 0; i < SPP; ++i) {
@@ -57,6 +61,25 @@ void run(const uint32_t* nodes, int max_depth, const FrameParams& fp, uint64_t r
 }
 }  // namespace
 
+static std::vector<uint32_t> g_top, g_bricks;
+static GridDev g_grid{nullptr, nullptr, 0};
+static bool g_grid_on = false;
+
+// Build (or drop, child == NULL) the sparse brick grid used by subsequent host_ray_walk calls.
+// Returns K (0 = not built for this depth), n_bricks through *n_bricks.
+extern "C" int host_ray_set_grid(const int32_t* child, const uint16_t* data, int data_dim, int64_t capacity, int max_depth,
+                                 int64_t* n_bricks) {
+    g_grid_on = false;
+    if (!child) return 0;
+    int K = 0;
+    if (!build_grid_host(child, data, data_dim, capacity, max_depth, g_top, g_bricks, K)) return 0;
+    if (g_bricks.empty()) g_bricks.assign(512, 0u);
+    g_grid = GridDev{g_top.data(), g_bricks.data(), K};
+    g_grid_on = true;
+    if (n_bricks) *n_bricks = (int64_t)(g_bricks.size() / 512);
+    return K;
+}
+
 extern "C" int host_ray_walk(const uint32_t* nodes, int max_depth, const float* c2w12, const float* offset,
                              const float* scale, float fx, float fy, float ndc_w, float ndc_h, float ndc_f,
                              float step_size, float sigma_thresh, int W, int H, int spp, uint64_t rng_state,
@@ -69,7 +92,7 @@ extern "C" int host_ray_walk(const uint32_t* nodes, int max_depth, const float* 
     for (int i = 0; i < 3; ++i) { fp.offset[i] = offset[i]; fp.scale[i] = scale[i]; }
     fp.fx = fx; fp.fy = fy; fp.ndc_width = ndc_w; fp.ndc_height = ndc_h; fp.ndc_focal = ndc_f;
     fp.step_size = step_size; fp.sigma_thresh = sigma_thresh; fp.background = 1.f; fp.W = W; fp.H = H;
-#define CASE(S) case S: run<S>(nodes, max_depth, fp, rng_state, rng_inc, pix_begin, pix_end, thresh, steps, term, src_bits, t_bits, leaf_hash, depth_sum, n_hits, n_loads, hit_leaf, hit_cnt, leaf_seq, max_seq); return 0;
+#define CASE(S) case S: run<S>(nodes, g_grid_on ? &g_grid : nullptr, max_depth, fp, rng_state, rng_inc, pix_begin, pix_end, thresh, steps, term, src_bits, t_bits, leaf_hash, depth_sum, n_hits, n_loads, hit_leaf, hit_cnt, leaf_seq, max_seq); return 0;
     switch (spp) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(6) CASE(8) CASE(16) CASE(32) default: return -1; }
 #undef CASE
 }

@@ -220,3 +220,30 @@ def test_full_size_properties(capi, oracle):
         for key in TRACE_KEYS:
             assert np.array_equal(g[key][b:e], o[key]), key
         assert np.abs(aux[:, y] - o["aux"][:, y]).max() < 1e-5
+
+
+@pytest.mark.parametrize("spp", [1, 6, 16])
+def test_grid_kernel_equals_tree_walker(capi, oracle, mid_tree, poses8, spp):
+    """The production (non-trace) kernel marches over the sparse brick grid; the TRACE kernel walks the tree.  Same hits
+    => same shading code => the aux buffers must be BIT-identical, and both equal the oracle's alpha."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H = 240, 176
+    fx = S.blender_focal(W)
+    t, ctx, cam = _setup(capi, mid_tree, W, H, fx)
+    i = t.info
+    assert i.grid_level == i.max_depth - 3 and i.n_bricks > 0 and i.grid_bytes > 0
+    for pi in (2, 7):
+        cam.transform = poses8[pi]
+        ctx.rng_set_frame(pi)
+        capi.launch_renderer(t, cam, _opts(capi, spp), ctx)                 # grid path
+        aux_grid = ctx.read_aux().copy()
+        img_grid = ctx.read_image().copy()
+        tr = GpuTrace(capi, W * H, spp)
+        capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)   # tree walker
+        g = tr.host()
+        assert np.array_equal(ctx.read_aux(), aux_grid)
+        assert np.array_equal(ctx.read_image(), img_grid)
+        o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, oracle.frame_rng(pi), thresh=g["thresh"], trace=False)
+        assert np.array_equal(aux_grid[3], o["aux"][3]) and np.abs(aux_grid - o["aux"]).max() < 1e-5
+        assert aux_grid[3].max() == 1.0

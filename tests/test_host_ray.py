@@ -75,3 +75,45 @@ def test_empty_and_degenerate_trees(oracle, host_ray_lib, poses8):
             assert o["aux"][3].max() == 0.0 and np.all(o["aux"][:3] == 1.0)   # pure background
         else:
             assert o["aux"][3].max() == 1.0
+
+
+@pytest.mark.parametrize("spp", [1, 6, 32])
+def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp):
+    """The sparse brick grid walker (rto_ray.cuh walk_grid: 1-2 loads per step, no descent) against the oracle; the VERIFY
+    build also checks at every step that the grid's (depth, sigma) equal the tree's (term == -777 flags a mismatch)."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H = 120, 90
+    fx = S.blender_focal(W)
+    for pi in (0, 5):
+        rng = oracle.frame_rng(pi)
+        o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48)
+        h = host_walk(host_ray_lib, mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48, grid=True)
+        assert not (h["term"] == -777).any(), "grid (depth, sigma) disagrees with the tree"
+        for k in TRACE_KEYS + ("leaf_seq",):
+            assert np.array_equal(h[k], o[k]), (k, spp, pi)
+        assert h["n_loads"].sum() <= 2 * o["steps"].sum()
+
+
+def test_host_grid_walk_other_depths(oracle, host_ray_lib, poses8):
+    """Depth 4 (K = 1, the shallowest gridded tree), depth 6 with anisotropic scale + NDC."""
+    from rt_octree_b200 import synthetic as S
+
+    t4 = S.make_tree(depth=4, shell=1.0, halo=0.3, seed=9)
+    W, H = 64, 48
+    fx = S.blender_focal(W)
+    rng = oracle.frame_rng(1)
+    o = oracle.render(t4, poses8[1], W, H, fx, fx, 6, rng)
+    h = host_walk(host_ray_lib, t4, poses8[1], W, H, fx, fx, 6, rng, grid=True)
+    assert not (h["term"] == -777).any()
+    for k in TRACE_KEYS:
+        assert np.array_equal(h[k], o[k]), k
+    tree = S.make_tree(depth=6, shell=1.0, halo=0.05, seed=5, invradius3=(0.45, 0.3, 0.5), offset=(0.5, 0.45, 0.55))
+    fx = 60.0
+    ndc = (float(W), float(H), fx)
+    pose = S.poses_to_c2w12(np.stack([S.look_at_pose((0.1, 0.05, 0.2), target=(0.0, 0.0, -1.0), world_up=(0, 1, 0))]))[0]
+    o = oracle.render(tree, pose, W, H, fx, fx, 6, rng, ndc=ndc)
+    h = host_walk(host_ray_lib, tree, pose, W, H, fx, fx, 6, rng, ndc=ndc, grid=True)
+    assert not (h["term"] == -777).any()
+    for k in TRACE_KEYS:
+        assert np.array_equal(h[k], o[k]), k

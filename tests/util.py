@@ -27,8 +27,17 @@ def tree_depth(tree):
 
 
 def host_walk(lib, tree, c2w12, W, H, fx, fy, spp, rng, ndc=(-1.0, 0.0, 0.0), step_size=1e-4, sigma_thresh=1e-2,
-              thresh=None, max_seq=0, pix_range=None):
+              thresh=None, max_seq=0, pix_range=None, grid=False):
+    """grid=True: march over the sparse brick grid (walk_grid, VERIFY build) instead of the ancestor-stack walker."""
     nodes = encode_nodes(tree)
+    if grid:
+        child = np.ascontiguousarray(tree["child"].reshape(-1), np.int32)
+        data = np.ascontiguousarray(tree["data"].reshape(-1)).view(np.uint16)
+        nb = C.c_int64(0)
+        K = lib.host_ray_set_grid(child.ctypes.data, data.ctypes.data, int(tree["data_dim"]), child.size // 8, tree_depth(tree), C.byref(nb))
+        assert K > 0, "grid not built for this tree depth"
+    else:
+        lib.host_ray_set_grid(None, None, 0, 0, 0, None)
     b, e = pix_range if pix_range else (0, W * H)
     n = e - b
     out = dict(steps=np.zeros(n, np.uint32), term=np.zeros(n, np.int32), src_bits=np.zeros(n, np.uint32),

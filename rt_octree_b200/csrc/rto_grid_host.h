@@ -43,7 +43,7 @@ inline bool build_grid_host(const int32_t* child, const uint16_t* data, int data
                     uint32_t* br = bricks.data() + (size_t)it.brick * 512;
                     for (uint32_t a = 0; a < s; ++a)
                         for (uint32_t b = 0; b < s; ++b)
-                            for (uint32_t c = 0; c < s; ++c) br[((lx + a) << 6) | ((ly + b) << 3) | (lz + c)] = word;
+                            for (uint32_t c = 0; c < s; ++c) br[brick_cell_index(lx + a, ly + b, lz + c)] = word;
                 }
             } else {
                 int64_t brick = it.brick;

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtoctree_b200.so")
+LIB_PATH = os.environ.get("RTO_LIB", os.path.join(_HERE, "librtoctree_b200.so"))   # RTO_LIB: A/B builds while tuning
 
 RTO_OK, RTO_ERR_INVALID, RTO_ERR_UNSUPPORTED, RTO_ERR_CUDA, RTO_ERR_NOMEM = 0, -1, -2, -3, -4
 FORMAT_RGBA, FORMAT_SH, FORMAT_SG, FORMAT_ASG = 0, 1, 2, 3

@@ -357,7 +357,7 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     fp.step_size = opt->step_size; fp.sigma_thresh = opt->sigma_thresh; fp.background = opt->background_brightness;
     fp.W = c->W; fp.H = c->H;
     a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth,
-                          rto::GridDev{t->grid_top, t->grid_bricks, t->grid_K}};
+                          rto::GridDev{t->grid_top, t->grid_bricks, t->grid_K}, (size_t)t->n_bricks * 512 * sizeof(uint32_t)};
     a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;

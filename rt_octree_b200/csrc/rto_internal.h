@@ -17,6 +17,7 @@ struct TreeDev {
     int basis_dim;          // >0: SH with that many coefficients per channel ; <=0: RGBA leaves
     int max_depth;          // max child look-ups to reach a leaf (sizes the per-ray ancestor stack)
     GridDev grid;           // sparse brick grid (grid.K == 0: none)
+    size_t grid_brick_bytes;
 };
 
 struct TraceOut {           // all optional (nullptr); indexed by the FULL-FRAME pixel index

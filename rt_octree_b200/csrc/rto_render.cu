@@ -266,6 +266,42 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
     int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;
+    // Optional L2 persistence window over the brick array (RTO_L2_PERSIST=1): keeps the grid resident in the 126 MB L2
+    // while the per-frame buffers (aux, maps, image) stream through.
+    static int persist = -1;
+    if (persist < 0) {
+        const char* e = getenv("RTO_L2_PERSIST");
+        persist = (e && e[0] == '1') ? 1 : 0;
+        if (persist) {
+            int dev = 0, max_persist = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            if (max_persist <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) persist = 0;
+        }
+    }
+    if (persist && grid_path && a.tree.grid_brick_bytes > 0) {
+        int dev = 0, max_win = 0, max_persist = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        size_t bytes = a.tree.grid_brick_bytes;
+        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kBlockThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[0].val.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(a.tree.grid.bricks);
+        at[0].val.accessPolicyWindow.num_bytes = bytes;
+        at[0].val.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
+        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, a);
+    }
     kern<<<grid, kBlockThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }

@@ -247,3 +247,65 @@ def test_grid_kernel_equals_tree_walker(capi, oracle, mid_tree, poses8, spp):
         o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, oracle.frame_rng(pi), thresh=g["thresh"], trace=False)
         assert np.array_equal(aux_grid[3], o["aux"][3]) and np.abs(aux_grid - o["aux"]).max() < 1e-5
         assert aux_grid[3].max() == 1.0
+
+
+def test_tt_shaped_depth10_1080p(capi, oracle):
+    """BASELINE config 4 shape: anisotropic depth-10 tree, 1920x1080, OpenCV-convention poses through the tt loader math.
+    Size-independent properties on the full frame + bit-exact oracle on sampled rows."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=10, shell=0.03, halo=0.02, seed=1, invradius3=(0.30, 0.42, 0.36), offset=(0.5, 0.52, 0.48))
+    W, H = 1920, 1080
+    fx = 1166.0
+    poses = S.poses_to_c2w12(S.make_poses(200, radius=3.2, elevation_deg=20.0))
+    t, ctx, cam = _setup(capi, tree, W, H, fx)
+    i = t.info
+    assert i.max_depth == 10 and i.grid_level == 7
+    cam.transform = poses[41]
+    ctx.rng_set_frame(41)
+    spp = 6
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx)           # grid kernel
+    aux = ctx.read_aux().copy()
+    tr = GpuTrace(capi, W * H, spp)
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)
+    g = tr.host()
+    assert np.array_equal(ctx.read_aux(), aux)                    # grid == tree walker, bit for bit
+    k = np.rint(aux[3] * spp)
+    assert np.array_equal(np.float32(k) * np.float32(1.0 / spp), aux[3]) and np.array_equal(k.reshape(-1), g["hit_cnt"].sum(1))
+    assert np.array_equal(aux[4:], aux[:4] * aux[:4]) and aux[3].max() == 1.0
+    for y in (300, 540, 541, 800):
+        b, e = y * W, (y + 1) * W
+        o = oracle.render(tree, poses[41], W, H, fx, fx, spp, oracle.frame_rng(41), pix_range=(b, e), thresh=g["thresh"][b:e])
+        for key in TRACE_KEYS:
+            assert np.array_equal(g[key][b:e], o[key]), key
+        assert np.abs(aux[:, y] - o["aux"][:, y]).max() < 1e-5
+
+
+def test_4k_tile_split_bands(capi, mid_tree, poses8, net_weights):
+    """BASELINE config 5 shape on one GPU: 3840x2160 SPP 6 + denoise rendered as 8 row bands (+6-row halo) equals the
+    full frame bit for bit (the multi-GPU version gathers the bands with NCCL: tools/tile_split_check.py)."""
+    from rt_octree_b200 import sharding as SH, synthetic as S
+
+    W, H = 3840, 2160
+    fx = float(np.float32(S.blender_focal(W)))
+    t = capi.N3Tree(mid_tree)
+    cam = capi.Camera(W, H, fx, fx)
+    cam.transform = poses8[6]
+    o = _opts(capi, 6, denoise=True)
+    net = capi.Denoiser(net_weights)
+    ctx = capi.RenderContext(W, H)
+    ctx.rng_set_frame(6)
+    capi.launch_renderer(t, cam, o, ctx)
+    net.denoise(cam, ctx)
+    full = ctx.read_image().copy()
+    out = np.zeros_like(full)
+    for band in SH.tile_bands(H, 8):
+        c = capi.RenderContext(W, H)
+        c.rng_set_frame(6)
+        y0, y1 = SH.render_rows_for_band(band, H, True)
+        capi.launch_renderer(t, cam, o, c, rect=(0, y0, W, y1))
+        net.denoise(cam, c, rows=band)
+        out[band[0]:band[1]] = c.read_image()[band[0]:band[1]]
+        c.close()
+    assert np.array_equal(out, full)
+    assert np.isfinite(full).all() and np.all(full[..., 3] == 1.0)

@@ -371,6 +371,11 @@ def run_cuda_arm(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None   # DRAM bytes per launch of the render kernel from the committed ncu --set full capture
+        try:
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))["dram_bytes_per_launch"])
+        except Exception:
+            pass
         achieved = bytes_frame / (render_ms * 1e-3) / 1e9
         fps = world * K / (ms_total * 1e-3)
         line = {
@@ -392,7 +397,7 @@ def run_cuda_arm(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "render_kernel<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": bytes_frame, "per_frame": counters,
                          "note": "algorithmic bytes = reference-equivalent traffic (4*depth+2 per step, 54 per collided leaf, 32 aux per ray)"},

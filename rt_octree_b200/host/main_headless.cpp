@@ -460,14 +460,14 @@ int main(int argc, char* argv[]) {
 
     if (args.has("dry_run")) {
         rtohost::npz_t z = rtohost::npz_load(tree_path);
-        const rtohost::NpyArray& ch = z.at("child");
+        N3Tree::HostArrays h;
+        N3Tree::decode_npz(z, h);
         printf("{\"poses\": %zu, \"width\": %d, \"height\": %d, \"fx\": %.9g, \"fy\": %.9g, \"spp\": %d, \"denoise\": %s, "
-               "\"step_size\": %.9g, \"sigma_thresh\": %.9g, \"background\": %.9g, \"capacity\": %zu, \"data_dim\": %d, "
+               "\"step_size\": %.9g, \"sigma_thresh\": %.9g, \"background\": %.9g, \"capacity\": %d, \"data_dim\": %d, "
                "\"data_format\": \"%s\", \"child_fnv\": \"%016llx\", \"data_fnv\": \"%016llx\", \"pose0\": [",
                trans.size(), width, height, fx, fy, job.options.spp, job.options.denoise ? "true" : "false", job.options.step_size,
-               job.options.sigma_thresh, job.options.background_brightness, ch.shape[0], (int)z.at("data_dim").scalar_as_double(),
-               z.count("data_format") ? z.at("data_format").as_string().c_str() : "", (unsigned long long)fnv64(ch.bytes.data(), ch.bytes.size()),
-               z.count("data") ? (unsigned long long)fnv64(z.at("data").bytes.data(), z.at("data").bytes.size()) : 0ull);
+               job.options.sigma_thresh, job.options.background_brightness, h.capacity, h.data_dim, h.data_format.to_string().c_str(),
+               (unsigned long long)fnv64(h.child, h.n_child * 4), (unsigned long long)fnv64(h.data, h.n_child * (size_t)h.data_dim * 2));
         for (int i = 0; i < 12; ++i) printf("%s%.9g", i ? ", " : "", trans[0].m[i]);
         printf("], \"pose_last\": [");
         for (int i = 0; i < 12; ++i) printf("%s%.9g", i ? ", " : "", trans.back().m[i]);

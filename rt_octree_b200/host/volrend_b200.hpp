@@ -107,61 +107,67 @@ struct N3Tree {
         if (device) rto_check(rto_tree_set_ndc(device, use_ndc ? ndc_width : -1.f, ndc_height, ndc_focal), "rto_tree_set_ndc");
     }
 
+    // Everything load_npz derives from the file, before the upload (also used by `volrend_headless --dry_run`).
     struct HostArrays {
-        std::vector<unsigned char> data;   // fp16 [cap][N][N][N][data_dim]
+        int N = 0, data_dim = 0, capacity = 0;
+        DataFormat data_format;
+        std::array<float, 3> scale{}, offset{};
         const int32_t* child = nullptr;
+        const unsigned char* data = nullptr;      // fp16 [cap][N][N][N][data_dim]
+        size_t n_child = 0;
+        std::vector<unsigned char> decoded;       // owns `data` for quantised files
     };
 
-   private:
-    void load_npz(rtohost::npz_t& npz) {
+    // N3Tree::load_npz (src/n3tree.cpp:228-362) without the upload
+    static void decode_npz(rtohost::npz_t& npz, HostArrays& h) {
         auto need = [&](const char* k) -> rtohost::NpyArray& {
             auto it = npz.find(k);
             if (it == npz.end()) throw std::runtime_error(std::string("tree.npz: missing key '") + k + "'");
             return it->second;
         };
-        data_dim = (int)need("data_dim").scalar_as_double();
+        h.data_dim = (int)need("data_dim").scalar_as_double();
         if (npz.count("data_format")) {
-            data_format.parse(npz["data_format"].as_string());
-        } else if (data_dim == 4) {
-            data_format.format = DataFormat::RGBA;
-            data_format.basis_dim = -1;
+            h.data_format.parse(npz["data_format"].as_string());
+        } else if (h.data_dim == 4) {
+            h.data_format.format = DataFormat::RGBA;
+            h.data_format.basis_dim = -1;
             fprintf(stderr, "INFO: Legacy file with no format specifier; spherical basis disabled\n");
         } else {
-            data_format.format = DataFormat::SH;
-            data_format.basis_dim = (data_dim - 1) / 3;
+            h.data_format.format = DataFormat::SH;
+            h.data_format.basis_dim = (h.data_dim - 1) / 3;
             fprintf(stderr, "INFO: Legacy file with no format specifier; autodetect spherical harmonics order\n");
         }
-        fprintf(stderr, "INFO: Data format %s\n", data_format.to_string().c_str());
+        fprintf(stderr, "INFO: Data format %s\n", h.data_format.to_string().c_str());
         if (npz.count("invradius3")) {
             const rtohost::NpyArray& s = npz["invradius3"];
-            for (int i = 0; i < 3; ++i) scale[i] = s.word_size == 4 ? s.data<float>()[i] : (float)s.data<double>()[i];
+            for (int i = 0; i < 3; ++i) h.scale[i] = s.word_size == 4 ? s.data<float>()[i] : (float)s.data<double>()[i];
         } else {
-            scale[0] = scale[1] = scale[2] = (float)need("invradius").scalar_as_double();
+            h.scale[0] = h.scale[1] = h.scale[2] = (float)need("invradius").scalar_as_double();
         }
-        printf("INFO: Scale %f %f %f\n", scale[0], scale[1], scale[2]);
         {
             const rtohost::NpyArray& o = need("offset");
-            for (int i = 0; i < 3; ++i) offset[i] = o.word_size == 4 ? o.data<float>()[i] : (float)o.data<double>()[i];
+            for (int i = 0; i < 3; ++i) h.offset[i] = o.word_size == 4 ? o.data<float>()[i] : (float)o.data<double>()[i];
         }
         rtohost::NpyArray& child = need("child");
         if (child.word_size != 4 || child.shape.size() != 4) throw std::runtime_error("child must be int32 [cap,N,N,N]");
-        N = (int)child.shape[1];
-        if (N != 2) fprintf(stderr, "WARNING: N != 2 probably doesn't work.\n");
+        h.N = (int)child.shape[1];
+        h.child = child.data<int32_t>();
+        if (h.N != 2) fprintf(stderr, "WARNING: N != 2 probably doesn't work.\n");
+        const int N = h.N, data_dim = h.data_dim;
         const size_t n_child = child.shape[0] * (size_t)N * N * N;
-        std::vector<unsigned char> decoded;
-        const unsigned char* data_ptr = nullptr;
+        h.n_child = n_child;
         if (npz.count("quant_colors")) {   // median-cut codebook decode, src/n3tree.cpp:279-340
             fprintf(stderr, "INFO: Decoding quantized colors\n");
             const rtohost::NpyArray& qc = npz["quant_colors"];
             if (qc.word_size != 2) throw std::runtime_error("codebook must be stored in half precision");
             const rtohost::NpyArray& qm = need("quant_map");
-            capacity = (int)qm.shape[1];
+            h.capacity = (int)qm.shape[1];
             int n_basis = (int)qm.shape[0];
             if ((int)qc.shape[0] != n_basis) throw std::runtime_error("codebook and map basis numbers does not match");
             const int n_ret = npz.count("data_retained") ? (int)npz["data_retained"].shape[0] : 0;
             n_basis += n_ret;
-            decoded.assign(n_child * (size_t)data_dim * 2, 0);
-            uint16_t* out = reinterpret_cast<uint16_t*>(decoded.data());
+            h.decoded.assign(n_child * (size_t)data_dim * 2, 0);
+            uint16_t* out = reinterpret_cast<uint16_t*>(h.decoded.data());
             const uint16_t* sig = need("sigma").data<uint16_t>();
             const uint16_t* map = qm.data<uint16_t>();
             const uint16_t* col = qc.data<uint16_t>();
@@ -184,14 +190,22 @@ struct N3Tree {
                         for (int k = 0; k < 3; ++k) { out[boff] = c[k]; boff += n_basis; }
                     }
             }
-            data_ptr = decoded.data();
+            h.data = h.decoded.data();
         } else {
             const rtohost::NpyArray& d = need("data");
-            capacity = (int)d.shape[0];
+            h.capacity = (int)d.shape[0];
             if (d.word_size != 2) throw std::runtime_error("data must be stored in half precision");
-            data_ptr = d.bytes.data();
+            h.data = d.bytes.data();
         }
-        rto_check(rto_tree_create(&device, child.data<int32_t>(), data_ptr, capacity, N, data_dim, (int)data_format.format,
+    }
+
+   private:
+    void load_npz(rtohost::npz_t& npz) {
+        HostArrays h;
+        decode_npz(npz, h);
+        N = h.N; data_dim = h.data_dim; capacity = h.capacity; data_format = h.data_format; scale = h.scale; offset = h.offset;
+        printf("INFO: Scale %f %f %f\n", scale[0], scale[1], scale[2]);
+        rto_check(rto_tree_create(&device, h.child, h.data, capacity, N, data_dim, (int)data_format.format,
                                   data_format.basis_dim, offset.data(), scale.data()),
                   "rto_tree_create");
     }

@@ -25,3 +25,14 @@ def test_ts_module_equals_reference_module(tmp_path, net_weights):
     back = M.export_weights(p)
     for k in ("w1", "b1", "w2", "b2"):
         assert np.array_equal(back[k], net_weights[k])
+
+
+def test_export_weights_from_reference_ts(net_weights):
+    """ts_ref_cpu.ts was written by the REFERENCE's compact_and_compile (denoiser/network.py:170-208) in this container
+    (tools/make_golden.py): a traced closure whose weights are prim::Constant tensors.  The exporter must recover the
+    same four fp16 tensors as the reference module's own parameters."""
+    import make_ts_module as M
+
+    back = M.export_weights(os.path.join(ROOT, "tests", "golden", "ts_ref_cpu.ts"))
+    for k in ("w1", "b1", "w2", "b2"):
+        assert back[k].dtype == np.float16 and np.array_equal(back[k], net_weights[k]), k

@@ -52,6 +52,11 @@ def golden_guidance_net():
         except Exception as e:  # CPU half conv unsupported in this torch build
             print("fp16 CPU forward unavailable:", e)
             w16, g16, have16 = c32w, c32g, False
+    # the reference's own export path: compact_and_compile -> traced TorchScript (constants on CPU here)
+    torch.manual_seed(0)
+    model2 = net_mod.GuidanceNet(8, 32, 5, 2, 4).eval()
+    ts = net_mod.compact_and_compile(model2, "cpu")
+    torch.jit.save(ts, os.path.join(OUT, "ts_ref_cpu.ts"))
     np.savez(os.path.join(OUT, "guidance_net_ref.npz"),
              w1=w1.numpy(), b1=b1.numpy(), w2=w2.numpy(), b2=b2.numpy(), aux=aux[0].numpy(),
              weight_fp16=w16[0].float().numpy(), guidance_fp16=g16[0].float().numpy(), have_fp16=np.bool_(have16),

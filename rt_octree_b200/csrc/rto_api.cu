@@ -45,6 +45,9 @@ struct rto_context {
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
     int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
+    rto::AdvanceMap* adv = nullptr;  // [H + W] pcg32 jump-ahead tables for (adv_spp, adv_inc)
+    int adv_spp = 0;
+    uint64_t adv_inc = 0;
     rto::Pcg32 rng{};
     // Timer
     bool timing = false;
@@ -278,6 +281,7 @@ int rto_context_create(rto_context** out, int W, int H) {
     if (e == cudaSuccess) e = cudaMalloc(&c->img, px * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&c->weight_map, px * 6 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->guidance_map, px * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->adv, (size_t)(W + H) * sizeof(rto::AdvanceMap));
     if (e == cudaSuccess) e = cudaMalloc(&c->tile_counter, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(c->tile_counter, 0, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(c->aux, 0, px * 8 * sizeof(float));
@@ -296,7 +300,7 @@ int rto_context_create(rto_context** out, int W, int H) {
 }
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
-    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter);
+    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
         if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
@@ -362,6 +366,18 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;
     a.tile_counter = c->tile_counter;
+    if (c->adv_spp != opt->spp || c->adv_inc != c->rng.inc) {   // (re)build the jump-ahead tables: depends on W, spp, inc only
+        std::vector<rto::AdvanceMap> tab((size_t)c->H + c->W);
+        for (int y = 0; y < c->H; ++y) tab[y] = rto::pcg32_advance_map(c->rng.inc, (uint64_t)y * (uint64_t)c->W * (uint64_t)opt->spp);
+        for (int x = 0; x < c->W; ++x) tab[(size_t)c->H + x] = rto::pcg32_advance_map(c->rng.inc, (uint64_t)x * (uint64_t)opt->spp);
+        // stream-ordered w.r.t. earlier launches on the legacy stream semantics: plain synchronous copy (rare)
+        RTO_CUDA(cudaDeviceSynchronize());
+        RTO_CUDA(cudaMemcpy(c->adv, tab.data(), tab.size() * sizeof(rto::AdvanceMap), cudaMemcpyHostToDevice));
+        c->adv_spp = opt->spp;
+        c->adv_inc = c->rng.inc;
+    }
+    a.adv_rows = c->adv;
+    a.adv_cols = c->adv + c->H;
     // with the denoiser on, the final image comes from rto_denoise; the reference then renders into a separate
     // noisy surface whose rgb equals aux channels 0..2 (volrend.cu:188-192 vs :205-212), so nothing is lost here
     a.img = opt->denoise ? nullptr : c->img;

@@ -30,7 +30,7 @@ inline bool build_grid_host(const int32_t* child, const uint16_t* data, int data
             const int64_t e = it.node * 8 + o;
             const int32_t skip = child[e];
             if (skip == 0) {
-                const uint32_t word = RTO_LEAF_FLAG | ((uint32_t)d << 16) | data[e * data_dim + data_dim - 1];
+                const uint32_t word = RTO_LEAF_FLAG | ((uint32_t)(127 + d) << 23) | data[e * data_dim + data_dim - 1];
                 if (d <= K) {
                     const uint32_t s = 1u << (K - d);
                     for (uint32_t a = 0; a < s; ++a)

@@ -44,6 +44,8 @@ struct RenderArgs {
     float* aux;                    // [8][H][W] fp32
     float4* img;                   // [H][W] float4, may be nullptr
     int* tile_counter;             // [2] device ints owned by the context: next tile, finished warps (self re-arming)
+    const AdvanceMap* adv_rows;    // [H] pcg32 jump-ahead maps for iy*W*spp
+    const AdvanceMap* adv_cols;    // [W] ... for ix*spp
     TraceOut tr;
 };
 

@@ -19,6 +19,10 @@
 
 namespace rto {
 
+#ifndef RTO_RENDER_MIN_BLOCKS
+#define RTO_RENDER_MIN_BLOCKS 8   // __launch_bounds__ min blocks/SM of the production kernels (8 -> 64 registers)
+#endif
+
 constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
 constexpr int kBlockThreads = 128;         // 4 independent warps per block
 constexpr int kDefaultBlocksPerSM = 8;      // tuned on B200 (tools/sweep_blocks.sh: 4:0.66 5:0.60 6:0.56 8:0.52 ms)
@@ -68,7 +72,7 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
 // GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent; TRACE builds
 // always use the tree walker because they must report the leaf visited at every step.
 template <int SPP, bool TRACE, bool GRID>
-__global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 8 : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? RTO_RENDER_MIN_BLOCKS : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
     static_assert(!(TRACE && GRID), "trace builds use the tree walker");
     extern __shared__ uint32_t ray_smem[];
     __shared__ unsigned s_state;
@@ -99,7 +103,12 @@ __global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? 8 : 4))
             setup_ray(fp, ix, iy, rs);
             float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
             WalkOut wo;
-            if (rs.hit) sorted_thresholds<SPP>(a.rng_state, a.rng_inc, idx, mem);
+            if (rs.hit) {
+                // ctx.rng.advance(idx*SPP) (volrend.cu:157) through the row/column jump-ahead tables
+                const AdvanceMap rm = a.adv_rows[iy], cm = a.adv_cols[ix];
+                Pcg32 rng{cm.mult * (rm.mult * a.rng_state + rm.plus) + cm.plus, a.rng_inc};
+                sorted_thresholds_from<SPP>(rng, mem);
+            }
             if (TRACE && a.tr.thresh && rs.hit) {
                 for (int i = 0; i < SPP; ++i) a.tr.thresh[(size_t)idx * SPP + i] = mem.dst(i);
             }

@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
-# GPU tuning helper: A/B the render kernel variants (env-selected) on the bench workload.
+# GPU tuning helper: A/B the render kernel variants (env-selected) on the bench workload (pipelined and serial).
 cd "$(dirname "$0")/.."
-run() { python bench.py --steps 100 --warmup 5 --no-baselines 2>/dev/null | python -c "
+run() { python bench.py --steps 200 --warmup 10 --no-baselines $2 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('$1: fps %.0f render %.3f ms denoise %.3f ms' % (d['value'], d['stage_ms']['render'], d['stage_ms']['denoise']))"; }
-run "A default"
-RTO_L2_PERSIST=1 run "A + L2 persisting window on bricks"
-[ -f build/varB/librtoctree_b200.so ] && RTO_LIB=$PWD/build/varB/librtoctree_b200.so run "B branch-free lookup"
-RTO_DISABLE_GRID=1 run "tree walker (grid disabled)"
+run "A default (8 blocks, 64 regs), 2 streams"
+RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=10 run "B 40 regs, 10 blocks, 2 streams"
+RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=12 run "B 40 regs, 12 blocks, 2 streams"
+RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=12 run "B 40 regs, 12 blocks, serial" --serial

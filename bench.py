@@ -270,8 +270,9 @@ def run_cuda_arm(args):
     K, Wm = args.steps, max(args.warmup, 3)
     # frame sharding: rank r renders global frames r*K .. r*K+K-1 (weak scaling); rng is a pure function of the frame
     my_frames = [rank * K + i for i in range(K)]
-    ctxs = [capi.RenderContext(W, H) for _ in range(2)]
-    streams = [torch.cuda.Stream() for _ in range(2)]
+    NBUF = 3   # frames in flight for the end-to-end loop (the device-timed loop uses the first two)
+    ctxs = [capi.RenderContext(W, H) for _ in range(NBUF)]
+    streams = [torch.cuda.Stream() for _ in range(NBUF)]
     ctx = ctxs[0]
     s0 = streams[0].cuda_stream
 
@@ -334,18 +335,18 @@ def run_cuda_arm(args):
     del flush
 
     # ---- end to end through the public API with host buffers: pose from host memory, final image read back into
-    #      pinned host memory every frame; two contexts/streams so frame f's D2H overlaps frame f+1's kernels
-    pinned = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    #      pinned host memory every frame; three contexts/streams so frame f's D2H overlaps the next frames' kernels
+    pinned = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
     host_poses = np.ascontiguousarray(poses)            # pageable host memory, read per step
 
     def e2e_frame(i, f):
-        c, st = ctxs[i & 1], streams[i & 1]
+        c, st = ctxs[i % NBUF], streams[i % NBUF]
         st.synchronize()                                 # buffer i&1 is free again (its previous D2H finished)
         cam.transform = host_poses[f % len(poses)]
         c.rng_set_frame(f, WARMUP_RNG)
         capi.launch_renderer(tree_h, cam, opt, c, stream=st.cuda_stream)
         net.denoise(cam, c, stream=st.cuda_stream)
-        c.read_image(pinned[i & 1].numpy(), stream=st.cuda_stream, sync=False)
+        c.read_image(pinned[i % NBUF].numpy(), stream=st.cuda_stream, sync=False)
 
     for i in range(Wm):
         e2e_frame(i, my_frames[i % K])
@@ -356,7 +357,7 @@ def run_cuda_arm(args):
         e2e_frame(i, f)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    checksum = float(pinned[(K - 1) & 1].sum())
+    checksum = float(pinned[(K - 1) % NBUF].sum())
 
     # ---- reduce over ranks: max time
     tt = torch.tensor([ms_total, e2e_s * 1e3, cold_ms, stage_ms[0], stage_ms[1] + stage_ms[2]], device="cuda", dtype=torch.float64)

@@ -24,8 +24,13 @@ namespace rto {
 #endif
 
 constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
-constexpr int kBlockThreads = 128;         // 4 independent warps per block
-constexpr int kDefaultBlocksPerSM = 8;      // tuned on B200 (tools/sweep_blocks.sh: 4:0.66 5:0.60 6:0.56 8:0.52 ms)
+#ifndef RTO_BLOCK_WARPS
+#define RTO_BLOCK_WARPS 4            // warps per block = warp tiles per super-tile (4: 2x2 tiles = 16x8 px, 8: 4x2 = 32x8 px)
+#endif
+constexpr int kBlockWarps = RTO_BLOCK_WARPS;
+constexpr int kSuperX = kBlockWarps / 2, kSuperY = 2;   // warp tiles per super-tile in x / y
+constexpr int kBlockThreads = 32 * kBlockWarps;
+constexpr int kDefaultBlocksPerSM = 32 / kBlockWarps;      // tuned on B200 (tools/sweep_blocks.sh: 4:0.66 5:0.60 6:0.56 8:0.52 ms)
 
 // Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
 //   [0, D]            ancestor stack (D = tree max depth)
@@ -53,14 +58,14 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
         for (;;) {
             const unsigned old = atomicAdd(s_state, 1u);
             const unsigned k = old & 0xffu;
-            if (k < 4u) { r = (old & ~0xffu) | k; break; }
-            if (k == 4u) {   // this warp refills: claim a new super-tile, publish it with sub-tile 0 taken by itself
+            if (k < (unsigned)kBlockWarps) { r = (old & ~0xffu) | k; break; }
+            if (k == (unsigned)kBlockWarps) {   // this warp refills: claim a new super-tile, publish it with sub-tile 0 taken by itself
                 const unsigned nsid = (unsigned)atomicAdd(g_counter, 1);
                 atomicExch(s_state, (nsid << 8) | 1u);
                 r = nsid << 8;
                 break;
             }
-            while ((*reinterpret_cast<volatile unsigned*>(s_state) & 0xffu) > 4u) __nanosleep(32);   // refill in flight
+            while ((*reinterpret_cast<volatile unsigned*>(s_state) & 0xffu) > (unsigned)kBlockWarps) __nanosleep(32);   // refill in flight
         }
     }
     r = __shfl_sync(0xffffffffu, r, 0);
@@ -72,14 +77,14 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
 // GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent; TRACE builds
 // always use the tree walker because they must report the leaf visited at every step.
 template <int SPP, bool TRACE, bool GRID>
-__global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? RTO_RENDER_MIN_BLOCKS : 4)) render_kernel(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RENDER_MIN_BLOCKS : 4)) * 4 / kBlockWarps) render_kernel(const __grid_constant__ RenderArgs a) {
     static_assert(!(TRACE && GRID), "trace builds use the tree walker");
     extern __shared__ uint32_t ray_smem[];
     __shared__ unsigned s_state;
     const int lane = threadIdx.x & 31;
     const FrameParams& fp = a.fp;
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
-    const int supers_x = (rw + 2 * kTileW - 1) / (2 * kTileW), supers_y = (rh + 2 * kTileH - 1) / (2 * kTileH);
+    const int supers_x = (rw + kSuperX * kTileW - 1) / (kSuperX * kTileW), supers_y = (rh + kSuperY * kTileH - 1) / (kSuperY * kTileH);
     const int n_supers = supers_x * supers_y;
     SmemRay<SPP> mem{ray_smem + threadIdx.x, GRID ? 0 : a.tree.max_depth + 1};
     const uint32_t* __restrict__ nodes = a.tree.nodes;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(kBlockThreads, TRACE ? 4 : (SPP <= 8 ? RTO_REN
         const int sr = sid / supers_x, sc = sid - sr * supers_x;
         const int mid = supers_y >> 1;
         const int srow = (sr & 1) ? mid - 1 - (sr >> 1) : mid + (sr >> 1);
-        const int tc = sc * 2 + (sub & 1), row = srow * 2 + (sub >> 1);
+        const int tc = sc * kSuperX + (sub % kSuperX), row = srow * kSuperY + (sub / kSuperX);
         const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
         const int iy = a.y0 + row * kTileH + (lane / kTileW);
         if (ix < a.x1 && iy < a.y1) {
@@ -271,7 +276,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         occ_limit[v] = occ > 0 ? occ : 1;
         smem_set[v] = smem;
     }
-    const int n_supers = ((rw + 2 * kTileW - 1) / (2 * kTileW)) * ((rh + 2 * kTileH - 1) / (2 * kTileH));
+    const int n_supers = ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
     int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;

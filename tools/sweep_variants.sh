@@ -3,7 +3,6 @@
 cd "$(dirname "$0")/.."
 run() { python bench.py --steps 200 --warmup 10 --no-baselines $2 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('$1: fps %.0f render %.3f ms denoise %.3f ms' % (d['value'], d['stage_ms']['render'], d['stage_ms']['denoise']))"; }
-run "A default (8 blocks, 64 regs), 2 streams"
-RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=10 run "B 40 regs, 10 blocks, 2 streams"
-RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=12 run "B 40 regs, 12 blocks, 2 streams"
-RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=12 run "B 40 regs, 12 blocks, serial" --serial
+run "A default (4 warps/block, 8 blocks)"
+RTO_LIB=$PWD/build/varB/librtoctree_b200.so run "B 8 warps/block (32x8 super-tiles), 4 blocks"
+RTO_LIB=$PWD/build/varB/librtoctree_b200.so RTO_RENDER_BLOCKS_PER_SM=3 run "B 8 warps/block, 3 blocks"

@@ -167,6 +167,18 @@ int rto_net_forward(const rto_net* net, const float* aux_dev, int width, int hei
 int rto_filter(const float* weight_dev, const float* guidance_dev, const float* img_in_dev, int levels, int width,
                int height, float* img_out_dev, void* stream);
 
+/* ---- training side of the same op: Filtering::forward with requires_grad / Filtering::backward,
+ * denoiser/extension/filtering.cu:580-699 behind `_denoiser.filtering_autograd` (bindings.cpp:5-13).  One image per call
+ * (the reference loops over the batch on the host too).  rgb_filtered [L][H][W][4], max_map / inv_kernel_sum [L][H][W] are
+ * the per-level tensors the reference saves for backward (:207-217); grads are [L][H][W].  The backward GATHERS over the
+ * symmetric window instead of the reference's scatter + atomicAdd (:230-301): same sums, deterministic order. */
+int rto_filter_forward_save(const float* weight_dev, const float* guidance_dev, const float* img_in_dev, int levels, int width,
+                            int height, float* img_out_dev, float* rgb_filtered_dev, float* max_map_dev,
+                            float* inv_kernel_sum_dev, void* stream);
+int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, const float* weight_dev, const float* guidance_dev,
+                        const float* rgb_filtered_dev, const float* max_map_dev, const float* inv_kernel_sum_dev, int levels,
+                        int width, int height, float* grad_weight_dev, float* grad_guidance_dev, void* stream);
+
 /* ---- timer : RenderContext::Timer (render_context.hpp:122-213) ----
  * With timing enabled rto_render / rto_denoise bracket their launches with cudaEvents on `stream`;
  * rto_timer_record synchronises on the last stop event and accumulates (Timer::record).  ms[0..2] = mean

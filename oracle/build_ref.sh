@@ -11,6 +11,8 @@
 #   ref_driver         oracle/ref_driver.cpp (ours) linked against the same reference objects; it calls
 #                      volrend::launch_renderer / Denoiser::denoise and dumps aux + final float image
 #   volrend.ptx        PTX of the reference render kernel (read to pin the op sequence)
+#   _denoiser_ref.so   the reference's Python extension (denoiser/extension/bindings.cpp + filtering.cu) as the torch
+#                      extension module `_denoiser_ref`: the unmodified `filtering_autograd` forward + backward
 #   libref_cpu.so      host-compiled reference trace_ray/query/SH functions (oracle/ref_cpu_shim.cpp)
 #
 # Two build-time tweaks only (both outside the forward path): `-include cstdint` for imwrite.cpp
@@ -68,6 +70,17 @@ build_cuda_ref() {
   g++ -o "$OUT/volrend_headless" "$OUT/obj/main_headless.o" $LIBOBJ $LINK
   g++ -o "$OUT/ref_driver" "$OUT/obj/ref_driver.o" $LIBOBJ $LINK
   echo "built $OUT/volrend_headless and $OUT/ref_driver"
+  # the reference's own torch extension (what denoiser/network.py:12-46 JIT-builds), under a non-clashing module name
+  PYINC="$(python3 -c 'import sysconfig;print(sysconfig.get_paths()["include"])')"
+  if newer "$OUT/patched/filtering.cu" "$OUT/_denoiser_ref.so"; then
+    nvcc -std=c++17 -O3 $ARCH $TI -I "$PYINC" -I "$OUT/patched" -Xcompiler -fPIC -DTORCH_EXTENSION_NAME=_denoiser_ref \
+         -D_GLIBCXX_USE_CXX11_ABI=1 -c "$OUT/patched/filtering.cu" -o "$OUT/obj/filtering_pic.o" &
+    g++ -std=c++17 -O2 -w -fPIC $TI -I "$CUDA_HOME/include" -I "$PYINC" -I "$OUT/patched" -DTORCH_EXTENSION_NAME=_denoiser_ref \
+         -c "$REF/denoiser/extension/bindings.cpp" -o "$OUT/obj/bindings.o" &
+    wait
+    g++ -shared -o "$OUT/_denoiser_ref.so" "$OUT/obj/bindings.o" "$OUT/obj/filtering_pic.o" $LINK -ltorch_python
+    echo "built $OUT/_denoiser_ref.so"
+  fi
 }
 
 build_cpu_ref() {

@@ -56,7 +56,7 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_context_rng_advance", "rto_context_rng_set_frame", "rto_context_rng_get", "rto_context_read_aux",
     "rto_context_read_image", "rto_render", "rto_render_rect", "rto_render_trace",
     "rto_net_create", "rto_net_destroy", "rto_net_set_impl", "rto_net_set_bias_mode", "rto_denoise", "rto_denoise_rows", "rto_net_forward",
-    "rto_filter", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
+    "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
 ]
 
 _lib = None
@@ -109,6 +109,8 @@ def load(path: str = LIB_PATH):
     L.rto_denoise_rows.argtypes = [P, P, I, I, P]
     L.rto_net_forward.argtypes = [P, P, I, I, P, P, P]
     L.rto_filter.argtypes = [P, P, P, I, I, I, P, P]
+    L.rto_filter_forward_save.argtypes = [P, P, P, I, I, I, P, P, P, P, P]
+    L.rto_filter_backward.argtypes = [P, P, P, P, P, P, P, I, I, I, P, P, P]
     L.rto_timer_enable.argtypes = [P, I]
     L.rto_timer_reset.argtypes = [P]
     L.rto_timer_record.argtypes = [P, I]

@@ -511,6 +511,37 @@ int rto_filter(const float* weight_dev, const float* guidance_dev, const float* 
     return RTO_OK;
 }
 
+// ---- training side of the filter: forward that saves (rgb_filtered, max, 1/sum) per level, and the backward ----
+int rto_filter_forward_save(const float* weight_dev, const float* guidance_dev, const float* img_in_dev, int L, int W, int H,
+                            float* img_out_dev, float* rgb_filtered_dev, float* max_map_dev, float* inv_kernel_sum_dev,
+                            void* stream) {
+    if (!weight_dev || !guidance_dev || !img_in_dev || !img_out_dev || !rgb_filtered_dev || !max_map_dev || !inv_kernel_sum_dev)
+        return fail(RTO_ERR_INVALID, "NULL argument");
+    if (L < 1 || L > 6) return fail(RTO_ERR_UNSUPPORTED, "Kernel size == %d not supported.", L * 2 + 1);
+    if (W <= 0 || H <= 0) return fail(RTO_ERR_INVALID, "bad size");
+    cudaError_t e = rto::launch_filter_simt(img_in_dev, 1, 4, weight_dev, guidance_dev, L, W, H, 0, H,
+                                            reinterpret_cast<float4*>(img_out_dev), (cudaStream_t)stream,
+                                            reinterpret_cast<float4*>(rgb_filtered_dev), max_map_dev, inv_kernel_sum_dev);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return RTO_OK;
+}
+
+int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, const float* weight_dev, const float* guidance_dev,
+                        const float* rgb_filtered_dev, const float* max_map_dev, const float* inv_kernel_sum_dev, int L, int W,
+                        int H, float* grad_weight_dev, float* grad_guidance_dev, void* stream) {
+    if (!grad_output_dev || !img_in_dev || !weight_dev || !guidance_dev || !rgb_filtered_dev || !max_map_dev ||
+        !inv_kernel_sum_dev || !grad_weight_dev || !grad_guidance_dev)
+        return fail(RTO_ERR_INVALID, "NULL argument");
+    if (L < 1 || L > 6) return fail(RTO_ERR_UNSUPPORTED, "Kernel size == %d not supported.", L * 2 + 1);
+    if (W <= 0 || H <= 0) return fail(RTO_ERR_INVALID, "bad size");
+    cudaError_t e = rto::launch_filter_backward(grad_output_dev, img_in_dev, weight_dev, guidance_dev, rgb_filtered_dev, max_map_dev,
+                                                inv_kernel_sum_dev, L, W, H, grad_weight_dev, grad_guidance_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter backward launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return RTO_OK;
+}
+
 // test-only debug tap of the tensor-core kernel (not declared in the public header)
 int rto_debug_tc_dump(float* dev_buf) {
     RTO_CUDA(rto::denoise_tc_set_debug(dev_buf));

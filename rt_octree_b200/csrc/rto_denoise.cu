@@ -134,7 +134,9 @@ constexpr int kFW = 32, kFH = 16;
 __global__ void __launch_bounds__(kFW * kFH) filter_kernel(const float* __restrict__ rgb /* aux ch0..2 planes, or [H][W][4] */,
                                                            size_t chan_stride, int pix_stride, const float* __restrict__ weight,
                                                            const float* __restrict__ guidance, int L, int W, int H,
-                                                           int y0, int y1, float4* __restrict__ out) {
+                                                           int y0, int y1, float4* __restrict__ out,
+                                                           float4* __restrict__ save_rgb /* [L][H][W] or null */,
+                                                           float* __restrict__ save_max, float* __restrict__ save_inv) {
     extern __shared__ float smem[];
     const int R = L;  // max support
     const int TW = kFW + 2 * R, TH = kFH + 2 * R;
@@ -173,11 +175,70 @@ __global__ void __launch_bounds__(kFW * kFH) filter_kernel(const float* __restri
                 gg = __fmaf_rn(rt[TH * TW + q], k, gg);
                 b = __fmaf_rn(rt[2 * TH * TW + q], k, b);
             }
-        const float w = weight[l * HW + (size_t)gy * W + gx] * (1.0f / ksum);
+        const float inv = 1.0f / ksum;
+        if (save_rgb) {   // saved for backward (filtering.cu:207-217)
+            const size_t sp = l * HW + (size_t)gy * W + gx;
+            save_rgb[sp] = make_float4(r * inv, gg * inv, b * inv, 0.f);
+            save_max[sp] = mx;
+            save_inv[sp] = inv;
+        }
+        const float w = weight[l * HW + (size_t)gy * W + gx] * inv;
         // level 0 overwrites, levels >= 1 accumulate (filtering.cu:218-227): mul, then add
         o0 = __fadd_rn(o0, __fmul_rn(r, w)); o1 = __fadd_rn(o1, __fmul_rn(gg, w)); o2 = __fadd_rn(o2, __fmul_rn(b, w));
     }
     out[(size_t)gy * W + gx] = make_float4(o0, o1, o2, 1.0f);
+}
+
+// Backward of the kernel filter (training side; denoiser/extension/filtering.cu:230-301, 472-576).
+//   grad_weight_l(p)   = <dout(p), F_l(p)>                                     (grad_weight_accumulate)
+//   grad_guidance_l(q) = sum_{p : q in N_l(p)} w_l(p) k_l(p,q) <dout(p), rgb(q) - F_l(p)>,  k = exp(g_l(q) - max_l(p)) / Z_l(p)
+// The reference scatters the second sum with one thread per (p, tap) and atomicAdd; the window is symmetric, so here
+// each thread GATHERS its own q over the same taps: no atomics, deterministic summation order.
+__global__ void __launch_bounds__(256) filter_backward_kernel(const float4* __restrict__ dout, const float4* __restrict__ img_in,
+                                                              const float* __restrict__ weight, const float* __restrict__ guidance,
+                                                              const float4* __restrict__ rgb_f, const float* __restrict__ max_map,
+                                                              const float* __restrict__ inv_sum, int L, int W, int H,
+                                                              float* __restrict__ grad_weight, float* __restrict__ grad_guidance) {
+    const size_t HW = (size_t)W * H;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW * L) return;
+    const int l = (int)(i / HW);
+    const size_t q = i - (size_t)l * HW;
+    const int qx = (int)(q % W), qy = (int)(q / W);
+    const int S = l + 1;
+    {
+        const float4 d = dout[q], f = rgb_f[i];
+        grad_weight[i] = d.x * f.x + d.y * f.y + d.z * f.z;
+    }
+    const float g = guidance[i];
+    const float4 c = img_in[q];
+    float acc = 0.f;
+    for (int dy = -S; dy <= S; ++dy) {
+        const int py = qy + dy;
+        if (py < 0 || py >= H) continue;
+        for (int dx = -S; dx <= S; ++dx) {
+            const int px = qx + dx;
+            if (px < 0 || px >= W) continue;
+            const size_t p = (size_t)l * HW + (size_t)py * W + px;
+            const float k = __expf(g - max_map[p]) * inv_sum[p];
+            const float4 d = dout[(size_t)py * W + px], f = rgb_f[p];
+            float res = d.x * (c.x - f.x);
+            res += d.y * (c.y - f.y);
+            res += d.z * (c.z - f.z);
+            acc += res * (weight[p] * k);
+        }
+    }
+    grad_guidance[i] = acc;
+}
+
+cudaError_t launch_filter_backward(const float* dout, const float* img_in, const float* weight, const float* guidance,
+                                   const float* rgb_f, const float* max_map, const float* inv_sum, int L, int W, int H,
+                                   float* grad_weight, float* grad_guidance, cudaStream_t stream) {
+    const size_t n = (size_t)W * H * L;
+    filter_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(img_in), weight, guidance,
+        reinterpret_cast<const float4*>(rgb_f), max_map, inv_sum, L, W, H, grad_weight, grad_guidance);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_guidance_net_simt(const NetDev& net, const DenoiseArgs& d, cudaStream_t stream) {
@@ -201,14 +262,15 @@ cudaError_t launch_guidance_net_simt(const NetDev& net, const DenoiseArgs& d, cu
 
 cudaError_t launch_filter_simt(const float* rgb, size_t chan_stride, int pix_stride, const float* weight,
                                const float* guidance, int L, int W, int H, int y0, int y1, float4* out,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, float4* save_rgb, float* save_max, float* save_inv) {
     const int rows = y1 - y0;
     if (rows <= 0) return cudaSuccess;
     dim3 grid((W + kFW - 1) / kFW, (rows + kFH - 1) / kFH), block(kFW, kFH);
     const size_t smem = sizeof(float) * (size_t)(3 + L) * (kFW + 2 * L) * (kFH + 2 * L);
     cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    filter_kernel<<<grid, block, smem, stream>>>(rgb, chan_stride, pix_stride, weight, guidance, L, W, H, y0, y1, out);
+    filter_kernel<<<grid, block, smem, stream>>>(rgb, chan_stride, pix_stride, weight, guidance, L, W, H, y0, y1, out, save_rgb,
+                                                 save_max, save_inv);
     return cudaGetLastError();
 }
 

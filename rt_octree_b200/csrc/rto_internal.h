@@ -77,5 +77,9 @@ cudaError_t launch_guidance_net_simt(const NetDev& net, const DenoiseArgs& d, cu
 // rgb[c*chan_stride + p*pix_stride]: (HW,1) for the planar aux buffer, (1,4) for an interleaved [H][W][4] image
 cudaError_t launch_filter_simt(const float* rgb, size_t chan_stride, int pix_stride, const float* weight,
                                const float* guidance, int L, int W, int H, int y0, int y1, float4* out,
-                               cudaStream_t stream);
+                               cudaStream_t stream, float4* save_rgb = nullptr, float* save_max = nullptr,
+                               float* save_inv = nullptr);
+cudaError_t launch_filter_backward(const float* dout, const float* img_in, const float* weight, const float* guidance,
+                                   const float* rgb_f, const float* max_map, const float* inv_sum, int L, int W, int H,
+                                   float* grad_weight, float* grad_guidance, cudaStream_t stream);
 }  // namespace rto

@@ -130,6 +130,9 @@ int rto_context_rng_set_frame(rto_context* ctx, int64_t warmup, int64_t frame);
 int rto_context_rng_get(const rto_context* ctx, uint64_t* state, uint64_t* inc);
 /* cudaMemcpy(…, DeviceToHost) of aux (main_headless.cpp:516-517) / image (:526-534); async on `stream`. */
 int rto_context_read_aux(rto_context* ctx, float* host_dst, void* stream);
+/* upload a stored guidance buffer (`buf_<name>.bin` of --write_buffer, fp32 [8][H][W]; denoiser/dataset.py:161-163 reads the
+ * same layout) so that rto_denoise can run on it without rendering */
+int rto_context_write_aux(rto_context* ctx, const float* host_src, void* stream);
 int rto_context_read_image(rto_context* ctx, float* host_dst, void* stream);
 
 /* ---- render : volrend::launch_renderer(tree, cam, options, ctx, stream, offscreen=true)

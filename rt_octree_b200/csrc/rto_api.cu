@@ -25,7 +25,6 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
                                float4* out, cudaStream_t stream);
 size_t denoise_tc_packed_bytes();
 cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream);
-cudaError_t denoise_tc_set_debug(float* p);
 }  // namespace rto
 
 struct rto_tree {
@@ -45,6 +44,12 @@ struct rto_context {
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
     int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
+    // feedback tile order of the production kernel: this frame's per-super-tile costs order the next frame's claims
+    uint32_t* tile_cost = nullptr;
+    uint32_t* tile_order = nullptr;
+    int order_cap = 0;              // allocated entries
+    int order_key[6] = {0, 0, 0, 0, 0, 0};   // x0,y0,x1,y1,spp,valid of the frame that produced tile_order
+    const void* order_tree = nullptr;
     rto::AdvanceMap* adv = nullptr;  // [H + W] pcg32 jump-ahead tables for (adv_spp, adv_inc)
     int adv_spp = 0;
     uint64_t adv_inc = 0;
@@ -300,7 +305,7 @@ int rto_context_create(rto_context** out, int W, int H) {
 }
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
-    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
+    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv); cudaFree(c->tile_cost); cudaFree(c->tile_order);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
         if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
@@ -334,6 +339,11 @@ int rto_context_rng_get(const rto_context* c, uint64_t* state, uint64_t* inc) {
 int rto_context_read_aux(rto_context* c, float* dst, void* stream) {
     if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
     RTO_CUDA(cudaMemcpyAsync(dst, c->aux, (size_t)c->W * c->H * 8 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RTO_OK;
+}
+int rto_context_write_aux(rto_context* c, const float* src, void* stream) {
+    if (!c || !src) return fail(RTO_ERR_INVALID, "NULL argument");
+    RTO_CUDA(cudaMemcpyAsync(c->aux, src, (size_t)c->W * c->H * 8 * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return RTO_OK;
 }
 int rto_context_read_image(rto_context* c, float* dst, void* stream) {
@@ -387,13 +397,41 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
                              trace->leaf_seq, trace->thresh, trace->max_seq};
     }
     cudaStream_t s = (cudaStream_t)stream;
+    // Feedback tile order (production kernel only): consecutive frames of a pose sequence are similar, so the costs
+    // measured in this frame order the next one.  Scheduling only - pixel values do not depend on it.
+    static int lpt = -1;
+    if (lpt < 0) { const char* v = getenv("RTO_TILE_LPT"); lpt = (v && v[0] == '0') ? 0 : 1; }
+    int n_supers = 0;
+    if (lpt && !trace && t->grid_K > 0 && x1 > x0 && y1 > y0) {
+        n_supers = rto::render_num_supers(x1 - x0, y1 - y0);
+        if (n_supers > c->order_cap) {
+            RTO_CUDA(cudaStreamSynchronize(s));
+            cudaFree(c->tile_cost); cudaFree(c->tile_order);
+            c->tile_cost = c->tile_order = nullptr; c->order_cap = 0; c->order_key[5] = 0;
+            RTO_CUDA(cudaMalloc(&c->tile_cost, (size_t)n_supers * sizeof(uint32_t)));
+            RTO_CUDA(cudaMalloc(&c->tile_order, (size_t)n_supers * sizeof(uint32_t)));
+            c->order_cap = n_supers;
+        }
+        const int key[6] = {x0, y0, x1, y1, opt->spp, 1};
+        const bool same = memcmp(key, c->order_key, sizeof key) == 0 && c->order_tree == (const void*)t;
+        if (!same) RTO_CUDA(cudaMemsetAsync(c->tile_cost, 0, (size_t)n_supers * sizeof(uint32_t), s));
+        a.tile_cost = c->tile_cost;
+        a.tile_order = same ? c->tile_order : nullptr;
+        memcpy(c->order_key, key, sizeof key);
+        c->order_tree = t;
+    }
     timer_start(c, 0, s);
     bool bad_spp = false;
     cudaError_t e = rto::launch_render(a, opt->spp, trace != nullptr, s, &bad_spp);
     timer_stop(c, 0, s);
-    if (bad_spp) return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp);
-    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
+    if (bad_spp) { c->order_key[5] = 0; return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp); }
+    if (e != cudaSuccess) { c->order_key[5] = 0; return fail(RTO_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e)); }
     ++g_launches;
+    if (a.tile_cost) {
+        e = rto::launch_tile_order(c->tile_cost, c->tile_order, n_supers, s);
+        if (e != cudaSuccess) { c->order_key[5] = 0; return fail(RTO_ERR_CUDA, "tile order launch: %s", cudaGetErrorString(e)); }
+        ++g_launches;
+    }
     return RTO_OK;
 }
 int rto_render(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt, void* stream) {
@@ -542,11 +580,6 @@ int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, c
     return RTO_OK;
 }
 
-// test-only debug tap of the tensor-core kernel (not declared in the public header)
-int rto_debug_tc_dump(float* dev_buf) {
-    RTO_CUDA(rto::denoise_tc_set_debug(dev_buf));
-    return RTO_OK;
-}
 
 // ---------------------------------------------------------------------------------------------------- timer
 int rto_timer_enable(rto_context* c, int enable) {

@@ -22,6 +22,7 @@
 // e^{g} precomputed once per pixel and level (guidance is in [0,6] after relu6, so the reference's max-subtraction
 // is not needed for range) and 4 output rows per thread sharing their taps.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -33,24 +34,33 @@
 namespace rto {
 
 namespace tc {
-constexpr int TW = 60, TH = 12, PW = 64;          // output tile, smem pitch (= TW + 4)
-constexpr int IN_PX = (TH + 4) * PW + 64;         // staged input pixels (+ slack read only by discarded rows)
-constexpr int MID_PX = 1024;                      // positions per 8-channel plane of the conv1 activation
-constexpr int Q1_MIN = PW + 1, N1_TILES = 7;      // conv1 positions [65, 961): x in [1,62], y in [1,14]
-constexpr int Q2_MIN = 2 * PW + 2, N2_TILES = 6;  // conv2 positions [130, 898): x in [2,61], y in [2,13]
-constexpr int THREADS = 256;
+constexpr int TW = 60, PW = 64;                   // output tile width, smem pitch (= TW + 4)
+constexpr int THREADS = 288;                      // warps 0-7: staging + epilogues (two teams of 4), warp 8: MMA issue
 constexpr int TMEM_COLS = 256;
 
-// shared memory map (bytes)
-constexpr int OFF_IN = 0;
-constexpr int OFF_MID = OFF_IN + IN_PX * 16;              // 17408
-constexpr int OFF_W1 = OFF_MID + 4 * MID_PX * 16;         // + 65536
-constexpr int OFF_W2 = OFF_W1 + 9 * 512;
-constexpr int OFF_ZERO = OFF_W2 + 9 * 1024;               // zero block: must lie ABOVE every operand start address
-constexpr int OFF_BIAS = OFF_ZERO + 2048;
-constexpr int OFF_BAR = OFF_BIAS + 40 * 4;
-constexpr int OFF_TMEM = OFF_BAR + 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 8;
+// Per tile height TH (rows of output pixels per CTA).  Positions are linear indices y*64+x into the staged tile.
+template <int TH>
+struct Cfg {
+    static constexpr int IN_PX = (TH + 4) * PW + 64;                       // staged input pixels (+ slack read only by discarded rows)
+    static constexpr int Q1_MIN = PW + 1;                                  // conv1 positions: x in [1,62], y in [1,TH+2]
+    static constexpr int N1_TILES = ((TH + 2) * PW - 2 + 127) / 128;
+    static constexpr int Q2_MIN = 2 * PW + 2;                              // conv2 positions: x in [2,61], y in [2,TH+1]
+    static constexpr int N2_TILES = (TH * PW - 4 + 127) / 128;
+    static constexpr int MID_PX = 128 * N1_TILES + 128;                    // positions per 8-channel plane of the conv1 activation
+    // shared memory map (bytes)
+    static constexpr int OFF_IN = 0;
+    static constexpr int OFF_MID = OFF_IN + IN_PX * 16;
+    static constexpr int OFF_W1 = OFF_MID + 4 * MID_PX * 16;
+    static constexpr int OFF_W2 = OFF_W1 + 9 * 512;
+    static constexpr int OFF_ZERO = OFF_W2 + 9 * 1024;                      // zero block: must lie ABOVE every operand start address
+    static constexpr int OFF_BIAS = OFF_ZERO + 2048;
+    static constexpr int OFF_BAR = OFF_BIAS + 40 * 4;                       // mbarriers: c1[N1] | mid[N1] | c2[N2]
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES);
+    static constexpr int SMEM_BYTES = OFF_TMEM + 8;
+    static_assert(N1_TILES * 32 <= TMEM_COLS, "conv1 accumulators must fit the TMEM allocation");
+    static_assert(128 * N1_TILES + 129 < IN_PX && 128 * N2_TILES + 194 < MID_PX, "operand reads stay inside the buffers");
+    static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
+};
 
 // packed weights in global memory: [w1: 9 taps][32 out][8 in] fp16 | [w2: 9 taps][4 chunks][16 out][8 in] fp16 |
 // b1 [32] fp32 | b2 [8] fp32
@@ -58,10 +68,6 @@ constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 9 * 1024, PK_BYTES =
 }  // namespace tc
 
 size_t denoise_tc_packed_bytes() { return tc::PK_BYTES; }
-
-// debug tap (tests only): when set, CTA (0,0) dumps its raw conv1 / conv2 accumulators: [1024][32] then [1024][8] floats
-__device__ float* g_tc_dbg = nullptr;
-cudaError_t denoise_tc_set_debug(float* p) { return cudaMemcpyToSymbol(g_tc_dbg, &p, sizeof(p)); }
 
 __global__ void pack_weights_kernel(const NetDev net, unsigned char* __restrict__ out) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +115,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -161,51 +170,94 @@ __device__ __forceinline__ uint32_t act_h2(float acc0, float acc1, float b0, flo
     return u;
 }
 
+__device__ __forceinline__ uint4 pack8(float c0, float c1, float c2, float c3, float c4, float c5, float c6, float c7) {
+    const __half2 h0 = __floats2half2_rn(c0, c1), h1 = __floats2half2_rn(c2, c3), h2 = __floats2half2_rn(c4, c5), h3 = __floats2half2_rn(c6, c7);
+    uint4 v;
+    memcpy(&v.x, &h0, 4); memcpy(&v.y, &h1, 4); memcpy(&v.z, &h2, 4); memcpy(&v.w, &h3, 4);
+    return v;
+}
+
+// One CTA = one 60 x TH tile, software-pipelined over its 128-position M-tiles with single-use mbarriers:
+//   warp 8 (one thread) issues every tcgen05.mma: conv1 tile i -> commit c1[i];  conv2 tile j once the activation
+//     tiles j..j+2 it reads are in shared memory (mid[]) -> commit c2[j];
+//   warps 0-7 form two epilogue teams of 4 warps (a warp can only read its own 32 TMEM lanes): team k handles conv1
+//     tiles k, k+2, ... (TMEM -> +b1, relu6, fp16 -> shared memory, arrive on mid[i]) and then conv2 tiles k, k+2, ...
+//     (TMEM -> +b2, relu6 -> softmax / guidance -> global).
+// The tensor pipe therefore runs conv1 of later tiles and conv2 of earlier tiles underneath both epilogues.
+template <int TH>
 __global__ void __launch_bounds__(tc::THREADS, 2)
 guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseArgs d, int fused_bias) {
     using namespace tc;
+    using C = Cfg<TH>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = d.W, H = d.H;
     const int bx = blockIdx.x * TW, by = d.y0 + blockIdx.y * TH;   // image coords of output pixel (x=2, y=2) of the tile
     const size_t HW = (size_t)W * H;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t bar = s_base + OFF_BAR;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+    const uint32_t bar_c1 = s_base + C::OFF_BAR, bar_mid = bar_c1 + 8 * C::N1_TILES, bar_c2 = bar_mid + 8 * C::N1_TILES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
-    // ---- one-time setup: TMEM allocation (warp 0), mbarrier (one thread)
+    // ---- one-time setup: TMEM allocation (warp 0), mbarriers (one thread)
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_base + OFF_TMEM), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_base + C::OFF_TMEM), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 32) {
-        mbar_init(bar, 1);
+        for (int i = 0; i < C::N1_TILES; ++i) { mbar_init(bar_c1 + 8 * i, 1); mbar_init(bar_mid + 8 * i, 128); }
+        for (int j = 0; j < C::N2_TILES; ++j) mbar_init(bar_c2 + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // ---- stage weights, zero block and the input tile (fp32 -> fp16, 8 channels = 16 B per pixel)
+    // ---- stage weights, zero block and the input tile (fp32 planes -> fp16, 8 channels = 16 B per pixel)
     {
         const uint4* src = reinterpret_cast<const uint4*>(packed);
-        uint4* w = reinterpret_cast<uint4*>(smem + OFF_W1);
+        uint4* w = reinterpret_cast<uint4*>(smem + C::OFF_W1);
         for (int i = tid; i < (PK_BIAS) / 16; i += THREADS) w[i] = __ldg(src + i);
-        float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+        float* bias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
         if (tid < 40) bias[tid] = __ldg(reinterpret_cast<const float*>(packed + PK_BIAS) + tid);
-        uint4* z = reinterpret_cast<uint4*>(smem + OFF_ZERO);
+        uint4* z = reinterpret_cast<uint4*>(smem + C::OFF_ZERO);
         if (tid < 128) z[tid] = make_uint4(0, 0, 0, 0);
-        uint4* in = reinterpret_cast<uint4*>(smem + OFF_IN);
-        for (int p = tid; p < IN_PX; p += THREADS) {
-            const int x = p & (PW - 1), y = p >> 6;
-            const int gx = bx + x - 2, gy = by + y - 2;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (y < TH + 4 && gx >= 0 && gx < W && gy >= 0 && gy < H) {
-                const float* a = d.aux + (size_t)gy * W + gx;
-                __half2 h0 = __floats2half2_rn(__ldg(a), __ldg(a + HW));
-                __half2 h1 = __floats2half2_rn(__ldg(a + 2 * HW), __ldg(a + 3 * HW));
-                __half2 h2 = __floats2half2_rn(__ldg(a + 4 * HW), __ldg(a + 5 * HW));
-                __half2 h3 = __floats2half2_rn(__ldg(a + 6 * HW), __ldg(a + 7 * HW));
-                v = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        uint4* in = reinterpret_cast<uint4*>(smem + C::OFF_IN);
+        const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0;
+        if (vec) {
+            // item = (row y, aligned group of 4 pixels): gx0 = bx - 4 + 4g covers tile-local x = 4g-2 .. 4g+1
+            constexpr int GROUPS = PW / 4 + 1;
+            for (int it = tid; it < (TH + 4) * GROUPS; it += THREADS) {
+                const int y = it / GROUPS, g = it - y * GROUPS;
+                const int gy = by + y - 2, gx0 = bx - 4 + 4 * g;
+                float4 c[8];
+                if (gy >= 0 && gy < H && gx0 >= 0 && gx0 < W) {
+                    const float* a = d.aux + (size_t)gy * W + gx0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) c[k] = __ldg(reinterpret_cast<const float4*>(a + k * HW));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const int x0 = 4 * g - 2;
+                uint4* row = in + y * PW;
+                if (x0 >= 0) {
+                    row[x0] = pack8(c[0].x, c[1].x, c[2].x, c[3].x, c[4].x, c[5].x, c[6].x, c[7].x);
+                    row[x0 + 1] = pack8(c[0].y, c[1].y, c[2].y, c[3].y, c[4].y, c[5].y, c[6].y, c[7].y);
+                }
+                if (x0 + 2 < PW) {
+                    row[x0 + 2] = pack8(c[0].z, c[1].z, c[2].z, c[3].z, c[4].z, c[5].z, c[6].z, c[7].z);
+                    row[x0 + 3] = pack8(c[0].w, c[1].w, c[2].w, c[3].w, c[4].w, c[5].w, c[6].w, c[7].w);
+                }
             }
-            in[p] = v;
+            for (int p = (TH + 4) * PW + tid; p < C::IN_PX; p += THREADS) in[p] = make_uint4(0, 0, 0, 0);
+        } else {
+            for (int p = tid; p < C::IN_PX; p += THREADS) {
+                const int x = p & (PW - 1), y = p >> 6;
+                const int gx = bx + x - 2, gy = by + y - 2;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (y < TH + 4 && gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                    const float* a = d.aux + (size_t)gy * W + gx;
+                    v = pack8(__ldg(a), __ldg(a + HW), __ldg(a + 2 * HW), __ldg(a + 3 * HW), __ldg(a + 4 * HW), __ldg(a + 5 * HW),
+                              __ldg(a + 6 * HW), __ldg(a + 7 * HW));
+                }
+                in[p] = v;
+            }
         }
     }
     fence_async_smem();
@@ -214,116 +266,121 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // ---- conv1: 7 M-tiles x 9 taps, D[128 x 32] += A[128 x 16] * B[32 x 16]^T
-    if (tid == 0) {
-        constexpr uint32_t idesc = make_idesc(32);
-        const uint32_t zero = s_base + OFF_ZERO;
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t zero = s_base + C::OFF_ZERO;
+            // ---- conv1: per M-tile 5 MMAs, D[128 x 32] += A[128 x 16] * B[32 x 16]^T.  The input has only 8 channels, so
+            // the two 8-wide K chunks of one MMA carry two filter taps: chunk 1 = chunk 0 shifted by LBO (one pixel to the
+            // right: 16 B, or one row down: 1024 B) in A and by whole 512-byte tap blocks in B.  Tap 8 pairs with zeros.
+            constexpr uint32_t idesc1 = make_idesc(32);
 #pragma unroll 1
-        for (int i = 0; i < N1_TILES; ++i) {
+            for (int i = 0; i < C::N1_TILES; ++i) {
+                const uint32_t pa = s_base + C::OFF_IN + (uint32_t)(C::Q1_MIN + 128 * i) * 16u;
+                const uint32_t pb = s_base + C::OFF_W1;
+                const uint32_t dcol = tmem + i * 32;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int shift = (t / 3 - 1) * PW + (t % 3 - 1);
-                const uint32_t a0 = s_base + OFF_IN + (uint32_t)(Q1_MIN + 128 * i + shift) * 16u;
-                const uint32_t b0 = s_base + OFF_W1 + t * 512;
-                umma_f16(tmem + i * 32, make_desc(a0, zero - a0, 128), make_desc(b0, zero - b0, 128), idesc, t > 0);
-            }
-        }
-        umma_commit(bar);
-    }
-    mbar_wait(bar, 0);
-    tc_fence_after();
-
-    // ---- epilogue 1: +b1, relu6, fp16 -> four 8-channel planes, zero outside the image
-    {
-        const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
-        const int row = (warp & 3) * 32 + lane;
-        for (int i = warp >> 2; i < N1_TILES; i += 2) {
-            uint32_t r[32];
-            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + i * 32, r);
-            const int q = Q1_MIN + 128 * i + row;
-            const int x = q & (PW - 1), y = q >> 6;
-            const int gx = bx + x - 2, gy = by + y - 2;
-            const bool inside = gx >= 0 && gx < W && gy >= 0 && gy < H;
-            if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && q < 1024)
-                for (int c = 0; c < 32; ++c) g_tc_dbg[q * 32 + c] = __uint_as_float(r[c]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = c * 8 + 2 * j;
-                    const uint32_t u = act_h2(__uint_as_float(r[ch]), __uint_as_float(r[ch + 1]), bias[ch], bias[ch + 1], fused_bias);
-                    pk[j] = inside ? u : 0u;
+                for (int r = 0; r < 3; ++r) {   // taps (dy, -1) + (dy, 0), dy = r - 1
+                    const uint32_t a0 = pa + (uint32_t)(((r - 1) * PW - 1) * 16);
+                    umma_f16(dcol, make_desc(a0, 16, 128), make_desc(pb + (3 * r) * 512, 512, 128), idesc1, r > 0);
                 }
-                if (q < MID_PX)
-                    *reinterpret_cast<uint4*>(smem + OFF_MID + (c * MID_PX + q) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                {   // taps (-1, +1) + (0, +1)
+                    const uint32_t a0 = pa + (uint32_t)((-PW + 1) * 16);
+                    umma_f16(dcol, make_desc(a0, PW * 16, 128), make_desc(pb + 2 * 512, 3 * 512, 128), idesc1, 1);
+                }
+                {   // tap (+1, +1) + zero chunk
+                    const uint32_t a0 = pa + (uint32_t)((PW + 1) * 16), b0 = pb + 8 * 512;
+                    umma_f16(dcol, make_desc(a0, zero - a0, 128), make_desc(b0, zero - b0, 128), idesc1, 1);
+                }
+                umma_commit(bar_c1 + 8 * i);
             }
-        }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0) {   // debug: what conv2 is about to read
-        const __half* m = reinterpret_cast<const __half*>(smem + OFF_MID);
-        for (int i = tid; i < 4 * MID_PX * 8; i += THREADS) g_tc_dbg[1024 * 40 + i] = __half2float(m[i]);
-        const __half* w = reinterpret_cast<const __half*>(smem + OFF_W2);
-        for (int i = tid; i < 9 * 512; i += THREADS) g_tc_dbg[1024 * 40 + 4 * MID_PX * 8 + i] = __half2float(w[i]);
-    }
-    // ---- conv2: 6 M-tiles x 9 taps x 2 k-steps, D[128 x 16] += A[128 x 16] * B[16 x 16]^T
-    if (tid == 0) {
-        constexpr uint32_t idesc = make_idesc(16);
+            // ---- conv2: per M-tile 9 taps x 2 k-steps, D[128 x 16] += A[128 x 16] * B[16 x 16]^T.  Tile j reads activation
+            // positions of conv1 tiles j..j+2, and its accumulator reuses TMEM columns of conv1 tile j/2, which the
+            // epilogue has finished reading by then.
+            constexpr uint32_t idesc2 = make_idesc(16);
+            int ready = 0;
 #pragma unroll 1
-        for (int j = 0; j < N2_TILES; ++j) {
+            for (int j = 0; j < C::N2_TILES; ++j) {
+                const int need = j + 2 < C::N1_TILES - 1 ? j + 2 : C::N1_TILES - 1;
+                for (; ready <= need; ++ready) mbar_wait(bar_mid + 8 * ready, 0);
+                tc_fence_after();
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int shift = (t / 3 - 1) * PW + (t % 3 - 1);
+                for (int t = 0; t < 9; ++t) {
+                    const int shift = (t / 3 - 1) * PW + (t % 3 - 1);
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const uint32_t a0 = s_base + OFF_MID + (uint32_t)(2 * s * MID_PX + Q2_MIN + 128 * j + shift) * 16u;
-                    const uint32_t b0 = s_base + OFF_W2 + t * 1024 + s * 512;
-                    umma_f16(tmem + j * 16, make_desc(a0, MID_PX * 16, 128), make_desc(b0, 256, 128), idesc, (t | s) > 0);
+                    for (int s = 0; s < 2; ++s) {
+                        const uint32_t a0 = s_base + C::OFF_MID + (uint32_t)(2 * s * C::MID_PX + C::Q2_MIN + 128 * j + shift) * 16u;
+                        const uint32_t b0 = s_base + C::OFF_W2 + t * 1024 + s * 512;
+                        umma_f16(tmem + j * 16, make_desc(a0, C::MID_PX * 16, 128), make_desc(b0, 256, 128), idesc2, (t | s) > 0);
+                    }
                 }
+                umma_commit(bar_c2 + 8 * j);
             }
         }
-        umma_commit(bar);
-    }
-    mbar_wait(bar, 1);
-    tc_fence_after();
-
-    // ---- epilogue 2: +b2, relu6, fp16 -> float ; softmax over the first 4 channels ; guidance = last 4
-    {
-        const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS) + 32;
-        const int row = (warp & 3) * 32 + lane;
-        for (int j = warp >> 2; j < N2_TILES; j += 2) {
-            uint32_t r[8];
-            tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + j * 16, r);
-            const int q = Q2_MIN + 128 * j + row;
-            const int x = q & (PW - 1), y = q >> 6;
-            const int gx = bx + x - 2, gy = by + y - 2;
-            if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && q < 1024)
-                for (int c = 0; c < 8; ++c) g_tc_dbg[1024 * 32 + q * 8 + c] = __uint_as_float(r[c]);
-            if (x >= 2 && x < TW + 2 && y >= 2 && y < TH + 2 && gx < W && gy < H && gy < d.y1) {
-                float o[8];
+        __syncwarp();   // lanes 1-31 wait for the issuing lane before the block-wide barrier below
+    } else {
+        const int team = warp >> 2, sub = warp & 3;
+        const int row = sub * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(sub * 32) << 16);
+        // ---- epilogue 1: +b1, relu6, fp16 -> four 8-channel planes, zero outside the image
+        {
+            const float* bias = reinterpret_cast<const float*>(smem + C::OFF_BIAS);
+            for (int i = team; i < C::N1_TILES; i += 2) {
+                mbar_wait(bar_c1 + 8 * i, 0);
+                tc_fence_after();
+                uint32_t r[32];
+                tmem_ld32(tlane + i * 32, r);
+                const int q = C::Q1_MIN + 128 * i + row;
+                const int x = q & (PW - 1), y = q >> 6;
+                const int gx = bx + x - 2, gy = by + y - 2;
+                const bool inside = gx >= 0 && gx < W && gy >= 0 && gy < H;
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    const uint32_t u = act_h2(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), bias[c], bias[c + 1], fused_bias);
-                    __half2 h;
-                    memcpy(&h, &u, 4);
-                    const float2 f = __half22float2(h);
-                    o[c] = f.x;
-                    o[c + 1] = f.y;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ch = c * 8 + 2 * j;
+                        const uint32_t u = act_h2(__uint_as_float(r[ch]), __uint_as_float(r[ch + 1]), bias[ch], bias[ch + 1], fused_bias);
+                        pk[j] = inside ? u : 0u;
+                    }
+                    *reinterpret_cast<uint4*>(smem + C::OFF_MID + (c * C::MID_PX + q) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
-                const float mx = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
-                float e[4], sum = 0.f;
+                fence_async_smem();    // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                tc_fence_before();     // orders this thread's tcgen05.ld before the MMAs that reuse the columns
+                mbar_arrive(bar_mid + 8 * i);
+            }
+        }
+        // ---- epilogue 2: +b2, relu6, fp16 -> float ; softmax over the first 4 channels ; guidance = last 4
+        {
+            const float* bias = reinterpret_cast<const float*>(smem + C::OFF_BIAS) + 32;
+            for (int j = team; j < C::N2_TILES; j += 2) {
+                mbar_wait(bar_c2 + 8 * j, 0);
+                tc_fence_after();
+                uint32_t r[8];
+                tmem_ld8(tlane + j * 16, r);
+                const int q = C::Q2_MIN + 128 * j + row;
+                const int x = q & (PW - 1), y = q >> 6;
+                const int gx = bx + x - 2, gy = by + y - 2;
+                if (x >= 2 && x < TW + 2 && y >= 2 && y < TH + 2 && gx < W && gy < H && gy < d.y1) {
+                    float o[8];
 #pragma unroll
-                for (int l = 0; l < 4; ++l) { e[l] = expf(o[l] - mx); sum += e[l]; }
-                const size_t p = (size_t)gy * W + gx;
+                    for (int c = 0; c < 8; c += 2) {
+                        const uint32_t u = act_h2(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), bias[c], bias[c + 1], fused_bias);
+                        __half2 h;
+                        memcpy(&h, &u, 4);
+                        const float2 f = __half22float2(h);
+                        o[c] = f.x;
+                        o[c + 1] = f.y;
+                    }
+                    const float mx = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
+                    float e[4], sum = 0.f;
 #pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    d.weight_map[l * HW + p] = e[l] / sum;
-                    d.guidance_map[l * HW + p] = o[4 + l];
+                    for (int l = 0; l < 4; ++l) { e[l] = expf(o[l] - mx); sum += e[l]; }
+                    const size_t p = (size_t)gy * W + gx;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        d.weight_map[l * HW + p] = e[l] / sum;
+                        d.guidance_map[l * HW + p] = o[4 + l];
+                    }
                 }
             }
         }
@@ -414,32 +471,174 @@ __global__ void __launch_bounds__(ff::THREADS) filter_fast_kernel(const float* _
     }
 }
 
-cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream) {
-    const int rows = d.y1 - d.y0;
-    if (rows <= 0) return cudaSuccess;
+// ------------------------------------------------------------------------------------------------ separable filter
+// The same sums as filter_fast_kernel, but sum_{q in N_l(p)} E_l(q) (rgb(q),1) is a BOX sum of the premultiplied field
+// E_l*(r,g,b,1), so it separates: a horizontal pass (registers, inputs straight from global/L2, 4 adjacent outputs per
+// thread) writes H_l[row][col] to shared memory, a vertical pass adds 2S+1 rows of H_l.  Work per pixel drops from
+// 164 taps x 4 FMA to 24 x 4 FMA (x 32/24 halo rows) + 24 x 4 FADD.  Summation order differs from the exact kernel
+// (fp32, <= 81 positive terms: relative 1e-6), well inside the 1e-3 image tolerance; rto_filter keeps the exact kernel.
+namespace fs {
+constexpr int BW = 32, BH = 24, R = 4, SROWS = BH + 2 * R;        // 32 staged rows
+constexpr int THREADS = 256;                                      // pass 1: 32 rows x 8 groups of 4 px ; pass 2: 32 cols x 8 groups of 3 rows
+constexpr int SMEM_BYTES = 4 * SROWS * BW * 16;                    // H[4][32][32] float4 = 64 KB
+static_assert(SROWS * (BW / 4) == THREADS && BW * (BH / 3) == THREADS, "thread mapping");
+}  // namespace fs
+
+__device__ __forceinline__ void load12(const float* __restrict__ plane, int W, bool vec, bool rowin, size_t rowoff, int xs,
+                                       float (&v)[12]) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int x = xs + 4 * s;
+        if (rowin && vec && x >= 0 && x + 3 < W) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(plane + rowoff + x));
+            v[4 * s] = t.x; v[4 * s + 1] = t.y; v[4 * s + 2] = t.z; v[4 * s + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[4 * s + k] = (rowin && x + k >= 0 && x + k < W) ? __ldg(plane + rowoff + x + k) : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float* __restrict__ aux, const float* __restrict__ weight,
+                                                                   const float* __restrict__ guidance, int W, int H, int y0,
+                                                                   int y1, float4* __restrict__ out) {
+    using namespace fs;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    float4* Hs = reinterpret_cast<float4*>(fsm);                  // [4][SROWS][BW], columns swizzled inside groups of 4
+    const int tid = threadIdx.x;
+    const int bx = blockIdx.x * BW, by = y0 + blockIdx.y * BH;
+    const size_t HW = (size_t)W * H;
+    const bool vec = (W & 3) == 0;                                // planes and rows 16-byte aligned
+    {   // ---- pass 1: horizontal sums of E_l * (r,g,b,1) for staged row r, outputs x = bx + 4*xg + j
+        const int r = tid >> 3, xg = tid & 7;
+        const int gy = by + r - R;
+        const int xs = bx + 4 * xg - R;
+        const bool rowin = gy >= 0 && gy < H;
+        const size_t rowoff = rowin ? (size_t)gy * W : 0;
+        float cr[12], cg[12], cb[12];
+        load12(aux, W, vec, rowin, rowoff, xs, cr);
+        load12(aux + HW, W, vec, rowin, rowoff, xs, cg);
+        load12(aux + 2 * HW, W, vec, rowin, rowoff, xs, cb);
+        const int sw = (xg >> 1) & 3;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int S = l + 1;
+            float e[12];
+            load12(guidance + l * HW, W, vec, rowin, rowoff, xs, e);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) e[i] = (rowin && xs + i >= 0 && xs + i < W) ? __expf(e[i]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int dx = -S; dx <= S; ++dx) {
+                    const int i = R + j + dx;
+                    a.x = fmaf(e[i], cr[i], a.x); a.y = fmaf(e[i], cg[i], a.y); a.z = fmaf(e[i], cb[i], a.z); a.w += e[i];
+                }
+                Hs[(l * SROWS + r) * BW + 4 * xg + (j ^ sw)] = a;   // swizzle: conflict-free 16-byte stores
+            }
+        }
+    }
+    __syncthreads();
+    {   // ---- pass 2: vertical sums, weights, output
+        const int x = tid & 31, ty = (tid >> 5) * 3;
+        const int slot = (x & ~3) | ((x & 3) ^ ((x >> 3) & 3));
+        const int gx = bx + x;
+        float o[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int S = l + 1;
+            float4 acc[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int rr = -S; rr <= 2 + S; ++rr) {
+                const float4 v = Hs[(l * SROWS + ty + R + rr) * BW + slot];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (rr - k >= -S && rr - k <= S) { acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w; }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int gy = by + ty + k;
+                if (gx < W && gy < H && gy < y1) {
+                    const float w = __ldg(weight + l * HW + (size_t)gy * W + gx) * (1.0f / acc[k].w);
+                    o[k][0] += acc[k].x * w; o[k][1] += acc[k].y * w; o[k][2] += acc[k].z * w;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int gy = by + ty + k;
+            if (gx < W && gy < H && gy < y1) out[(size_t)gy * W + gx] = make_float4(o[k][0], o[k][1], o[k][2], 1.0f);
+        }
+    }
+}
+
+template <int TH>
+static cudaError_t launch_net_th(const NetDev& net, const void* packed, const DenoiseArgs& d, int rows, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(guidance_net_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(guidance_net_tc_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TH>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + tc::TH - 1) / tc::TH);
-    guidance_net_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias);
+    dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + TH - 1) / TH);
+    guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias);
     return cudaGetLastError();
+}
+
+// Tile height: two CTAs are resident per SM (TMEM: 2 x 256 columns), so the launch runs in ceil(tiles / (2 * SMs)) rounds
+// of cost ~ (TH + 4) staged rows each; pick the height with the cheapest total (800 rows: 14 -> 3 rounds, 12 -> 4 rounds).
+cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream) {
+    const int rows = d.y1 - d.y0;
+    if (rows <= 0) return cudaSuccess;
+    static int num_sms = 0, forced = -1;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        const char* v = getenv("RTO_NET_TILE_H");
+        forced = v ? atoi(v) : 0;
+    }
+    const int cols = (d.W + tc::TW - 1) / tc::TW;
+    int best = 12;
+    long best_cost = -1;
+    for (int th : {14, 12, 10}) {
+        const long tiles = (long)cols * ((rows + th - 1) / th);
+        const long cost = ((tiles + 2 * num_sms - 1) / (2 * num_sms)) * (th + 4);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = th; }
+    }
+    if (forced == 10 || forced == 12 || forced == 14) best = forced;
+    switch (best) {
+        case 14: return launch_net_th<14>(net, packed, d, rows, stream);
+        case 10: return launch_net_th<10>(net, packed, d, rows, stream);
+        default: return launch_net_th<12>(net, packed, d, rows, stream);
+    }
 }
 
 cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
                                float4* out, cudaStream_t stream) {
     const int rows = y1 - y0;
     if (rows <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int impl = -1;   // RTO_FILTER_IMPL=taps selects the direct 164-tap kernel (A/B and debugging)
+    if (impl < 0) {
+        const char* v = getenv("RTO_FILTER_IMPL");
+        impl = (v && v[0] == 't') ? 1 : 0;
         cudaError_t e = cudaFuncSetAttribute(filter_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ff::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(filter_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs::SMEM_BYTES);
+        if (e != cudaSuccess) { impl = -1; return e; }
     }
-    dim3 grid((W + ff::BW - 1) / ff::BW, (rows + ff::BH - 1) / ff::BH);
-    filter_fast_kernel<<<grid, ff::THREADS, ff::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
+    if (impl == 1) {
+        dim3 grid((W + ff::BW - 1) / ff::BW, (rows + ff::BH - 1) / ff::BH);
+        filter_fast_kernel<<<grid, ff::THREADS, ff::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
+    } else {
+        dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
+        filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
+    }
     return cudaGetLastError();
 }
 

@@ -44,12 +44,6 @@ struct rto_context {
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
     int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
-    // feedback tile order of the production kernel: this frame's per-super-tile costs order the next frame's claims
-    uint32_t* tile_cost = nullptr;
-    uint32_t* tile_order = nullptr;
-    int order_cap = 0;              // allocated entries
-    int order_key[6] = {0, 0, 0, 0, 0, 0};   // x0,y0,x1,y1,spp,valid of the frame that produced tile_order
-    const void* order_tree = nullptr;
     rto::AdvanceMap* adv = nullptr;  // [H + W] pcg32 jump-ahead tables for (adv_spp, adv_inc)
     int adv_spp = 0;
     uint64_t adv_inc = 0;
@@ -224,7 +218,8 @@ int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, 
         std::vector<uint32_t> top, bricks;
         int K = 0;
         if (!(off && off[0] == '1') &&
-            rto::build_grid_host(child, static_cast<const uint16_t*>(data_f16), data_dim, capacity, max_depth, top, bricks, K)) {
+            rto::build_grid_host(child, static_cast<const uint16_t*>(data_f16), data_dim, capacity, max_depth, top, bricks, K) &&
+            bricks.size() / 512 < ((size_t)1 << 23)) {   // the marcher indexes brick words with 32 bits (rto_ray.cuh grid_lookup)
             cudaError_t ge = cudaMalloc(&t->grid_top, top.size() * sizeof(uint32_t));
             if (ge == cudaSuccess) ge = cudaMalloc(&t->grid_bricks, (bricks.empty() ? 512 : bricks.size()) * sizeof(uint32_t));
             if (ge == cudaSuccess) ge = cudaMemcpy(t->grid_top, top.data(), top.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
@@ -305,7 +300,7 @@ int rto_context_create(rto_context** out, int W, int H) {
 }
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
-    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv); cudaFree(c->tile_cost); cudaFree(c->tile_order);
+    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
         if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
@@ -371,7 +366,7 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     fp.step_size = opt->step_size; fp.sigma_thresh = opt->sigma_thresh; fp.background = opt->background_brightness;
     fp.W = c->W; fp.H = c->H;
     a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth,
-                          rto::GridDev{t->grid_top, t->grid_bricks, t->grid_K}, (size_t)t->n_bricks * 512 * sizeof(uint32_t)};
+                          rto::make_grid_dev(t->grid_top, t->grid_bricks, t->grid_K), (size_t)t->n_bricks * 512 * sizeof(uint32_t)};
     a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;
@@ -397,41 +392,13 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
                              trace->leaf_seq, trace->thresh, trace->max_seq};
     }
     cudaStream_t s = (cudaStream_t)stream;
-    // Feedback tile order (production kernel only): consecutive frames of a pose sequence are similar, so the costs
-    // measured in this frame order the next one.  Scheduling only - pixel values do not depend on it.
-    static int lpt = -1;
-    if (lpt < 0) { const char* v = getenv("RTO_TILE_LPT"); lpt = (v && v[0] == '0') ? 0 : 1; }
-    int n_supers = 0;
-    if (lpt && !trace && t->grid_K > 0 && x1 > x0 && y1 > y0) {
-        n_supers = rto::render_num_supers(x1 - x0, y1 - y0);
-        if (n_supers > c->order_cap) {
-            RTO_CUDA(cudaStreamSynchronize(s));
-            cudaFree(c->tile_cost); cudaFree(c->tile_order);
-            c->tile_cost = c->tile_order = nullptr; c->order_cap = 0; c->order_key[5] = 0;
-            RTO_CUDA(cudaMalloc(&c->tile_cost, (size_t)n_supers * sizeof(uint32_t)));
-            RTO_CUDA(cudaMalloc(&c->tile_order, (size_t)n_supers * sizeof(uint32_t)));
-            c->order_cap = n_supers;
-        }
-        const int key[6] = {x0, y0, x1, y1, opt->spp, 1};
-        const bool same = memcmp(key, c->order_key, sizeof key) == 0 && c->order_tree == (const void*)t;
-        if (!same) RTO_CUDA(cudaMemsetAsync(c->tile_cost, 0, (size_t)n_supers * sizeof(uint32_t), s));
-        a.tile_cost = c->tile_cost;
-        a.tile_order = same ? c->tile_order : nullptr;
-        memcpy(c->order_key, key, sizeof key);
-        c->order_tree = t;
-    }
     timer_start(c, 0, s);
     bool bad_spp = false;
     cudaError_t e = rto::launch_render(a, opt->spp, trace != nullptr, s, &bad_spp);
     timer_stop(c, 0, s);
-    if (bad_spp) { c->order_key[5] = 0; return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp); }
-    if (e != cudaSuccess) { c->order_key[5] = 0; return fail(RTO_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e)); }
+    if (bad_spp) return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
     ++g_launches;
-    if (a.tile_cost) {
-        e = rto::launch_tile_order(c->tile_cost, c->tile_order, n_supers, s);
-        if (e != cudaSuccess) { c->order_key[5] = 0; return fail(RTO_ERR_CUDA, "tile order launch: %s", cudaGetErrorString(e)); }
-        ++g_launches;
-    }
     return RTO_OK;
 }
 int rto_render(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt, void* stream) {

@@ -46,14 +46,9 @@ struct RenderArgs {
     int* tile_counter;             // [2] device ints owned by the context: next tile, finished warps (self re-arming)
     const AdvanceMap* adv_rows;    // [H] pcg32 jump-ahead maps for iy*W*spp
     const AdvanceMap* adv_cols;    // [W] ... for ix*spp
-    const uint32_t* tile_order;    // [n_supers] claim index -> super-tile id, heaviest first (nullptr: centre rows first)
-    uint32_t* tile_cost;           // [n_supers] max marching steps of any ray of the super-tile this frame (nullptr: off)
     TraceOut tr;
 };
 
-int render_num_supers(int rw, int rh);
-// builds next frame's claim order from this frame's costs (longest-processing-time-first) and clears the costs
-cudaError_t launch_tile_order(uint32_t* cost, uint32_t* order, int n, cudaStream_t stream);
 cudaError_t launch_render(const RenderArgs& a, int spp, bool trace, cudaStream_t stream, bool* bad_spp);
 
 // GuidanceNet (deployed form) weights on the device, fp16

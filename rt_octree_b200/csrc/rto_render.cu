@@ -95,18 +95,12 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
         int sid, sub;
         next_tile(&s_state, a.tile_counter, lane, sid, sub);
         if (sid >= n_supers) break;
-        // claim order: last frame's costs, heaviest first (the frame time is bounded by the longest serial chain, so the
-        // long tiles must start first); without history, centre rows first: 0 -> mid, 1 -> mid-1, 2 -> mid+1, ...
-        int sr, sc, srow;
-        if (a.tile_order) {
-            const int t = (int)__ldg(a.tile_order + sid);
-            srow = t / supers_x; sc = t - srow * supers_x;
-        } else {
-            sr = sid / supers_x; sc = sid - sr * supers_x;
-            const int mid = supers_y >> 1;
-            srow = (sr & 1) ? mid - 1 - (sr >> 1) : mid + (sr >> 1);
-        }
-        unsigned my_steps = 0;
+        // centre-first row order of super-tiles: 0 -> mid, 1 -> mid-1, 2 -> mid+1, ...  (A feedback order - last frame's
+        // per-tile step counts, heaviest first, rebuilt by a counting-sort kernel - was measured on B200: render 0.2728 vs
+        // 0.2795 ms, i.e. exactly the 6.5 us the extra sort launch costs; not kept.)
+        const int sr = sid / supers_x, sc = sid - sr * supers_x;
+        const int mid = supers_y >> 1;
+        const int srow = (sr & 1) ? mid - 1 - (sr >> 1) : mid + (sr >> 1);
         const int tc = sc * kSuperX + (sub % kSuperX), row = srow * kSuperY + (sub / kSuperX);
         const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
         const int iy = a.y0 + row * kTileH + (lane / kTileW);
@@ -133,7 +127,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             else
                 walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             const uint32_t sh_nums = wo.n_hits;
-            my_steps = wo.steps;
 
             if (TRACE) {
                 const TraceOut& tr = a.tr;
@@ -238,10 +231,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             if (a.img) a.img[idx] = make_float4(out0, out1, out2, 1.0f);
         }
         __syncwarp();
-        if (a.tile_cost) {
-            const unsigned m = __reduce_max_sync(0xffffffffu, my_steps);
-            if (lane == 0 && m) atomicMax(a.tile_cost + srow * supers_x + sc, m);
-        }
     }
     // the last warp to leave re-arms the counters for the next launch on this context
     if (lane == 0) {
@@ -252,49 +241,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             __threadfence();
         }
     }
-}
-
-int render_num_supers(int rw, int rh) {
-    return ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
-}
-
-// Counting sort of the super-tiles by cost (8-step buckets), heaviest first, in one block; clears the costs.
-__global__ void __launch_bounds__(1024) tile_order_kernel(uint32_t* __restrict__ cost, uint32_t* __restrict__ order, int n) {
-    constexpr int NB = 256;
-    __shared__ unsigned cnt[NB];
-    for (int i = threadIdx.x; i < NB; i += blockDim.x) cnt[i] = 0u;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned b = cost[i] >> 3;
-        atomicAdd(&cnt[NB - 1 - (b < NB - 1 ? b : NB - 1)], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {   // exclusive scan of 256 counters by one warp, 8 per lane
-        unsigned v[NB / 32], sum = 0u;
-#pragma unroll
-        for (int k = 0; k < NB / 32; ++k) { v[k] = cnt[threadIdx.x * (NB / 32) + k]; sum += v[k]; }
-        unsigned incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((int)threadIdx.x >= d) incl += o;
-        }
-        unsigned run = incl - sum;
-#pragma unroll
-        for (int k = 0; k < NB / 32; ++k) { cnt[threadIdx.x * (NB / 32) + k] = run; run += v[k]; }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned b = cost[i] >> 3;
-        const unsigned pos = atomicAdd(&cnt[NB - 1 - (b < NB - 1 ? b : NB - 1)], 1u);
-        order[pos] = (uint32_t)i;
-        cost[i] = 0u;
-    }
-}
-
-cudaError_t launch_tile_order(uint32_t* cost, uint32_t* order, int n, cudaStream_t stream) {
-    tile_order_kernel<<<1, 1024, 0, stream>>>(cost, order, n);
-    return cudaGetLastError();
 }
 
 // Resident blocks per SM of the persistent kernel.  More warps raise issue utilisation but every warp then advances
@@ -332,7 +278,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         occ_limit[v] = occ > 0 ? occ : 1;
         smem_set[v] = smem;
     }
-    const int n_supers = render_num_supers(rw, rh);
+    const int n_supers = ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
     int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;

@@ -74,7 +74,7 @@ extern "C" int host_ray_set_grid(const int32_t* child, const uint16_t* data, int
     int K = 0;
     if (!build_grid_host(child, data, data_dim, capacity, max_depth, g_top, g_bricks, K)) return 0;
     if (g_bricks.empty()) g_bricks.assign(512, 0u);
-    g_grid = GridDev{g_top.data(), g_bricks.data(), K};
+    g_grid = make_grid_dev(g_top.data(), g_bricks.data(), K);
     g_grid_on = true;
     if (n_bricks) *n_bricks = (int64_t)(g_bricks.size() / 512);
     return K;

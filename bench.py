@@ -270,7 +270,7 @@ def run_cuda_arm(args):
     K, Wm = args.steps, max(args.warmup, 3)
     # frame sharding: rank r renders global frames r*K .. r*K+K-1 (weak scaling); rng is a pure function of the frame
     my_frames = [rank * K + i for i in range(K)]
-    NBUF = 3   # frames in flight for the end-to-end loop (the device-timed loop uses the first two)
+    NBUF = max(3, args.pipe)   # frames in flight for the end-to-end loop (the device-timed loop uses the first --pipe)
     ctxs = [capi.RenderContext(W, H) for _ in range(NBUF)]
     streams = [torch.cuda.Stream() for _ in range(NBUF)]
     ctx = ctxs[0]
@@ -285,7 +285,7 @@ def run_cuda_arm(args):
     # ---- device-resident throughput: K frames, CUDA events, max over ranks.  Frames are independent, so they are
     #      issued alternately on two (context, stream) pairs: the long tail of one frame's render kernel (a few heavy
     #      warps) overlaps the next frame's start.  --serial uses one stream (the reference's protocol).
-    n_pipe = 1 if args.serial else 2
+    n_pipe = 1 if args.serial else args.pipe
     for i in range(Wm):
         frame(ctxs[i % n_pipe], my_frames[i % K], streams[i % n_pipe].cuda_stream)
     torch.cuda.synchronize()
@@ -421,6 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames timed for the cpu_baseline sample")
+    ap.add_argument("--pipe", type=int, default=4, help="frames in flight (contexts/streams) of the device-timed loop")
     ap.add_argument("--serial", action="store_true", help="one stream, frames strictly back to back (reference protocol)")
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / reference_cuda side measurements")
     args = ap.parse_args()

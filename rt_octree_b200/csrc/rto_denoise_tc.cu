@@ -2,8 +2,8 @@
 //
 // The two 3x3 convolutions of the deployed GuidanceNet (denoiser/network.py:123-168: conv 8->32, relu6, conv 32->8,
 // relu6, fp16 storage / fp32 accumulate) are the only dense contraction on the render path.  The reference runs
-// them through libtorch/cuDNN (src/denoiser/denoiser.cpp:46).  Here each CTA owns a 60x12 pixel tile and runs both
-// convolutions as implicit GEMMs with M = pixels, one tcgen05.mma per (M-tile, filter tap[, k-step]):
+// them through libtorch/cuDNN (src/denoiser/denoiser.cpp:46).  Here each CTA owns a 60 x TH pixel tile (TH = 10/12/14) and
+// runs both convolutions as implicit GEMMs with M = pixels:
 //
 //   * the tile (+2 px halo) is staged in shared memory PIXEL-MAJOR with a pitch of 64 pixels, 8 fp16 channels =
 //     one 16-byte row of a K-major / no-swizzle core matrix.  Because consecutive pixels are consecutive 16-byte
@@ -11,16 +11,19 @@
 //     is shifted by (dy*64+dx) pixels — no im2col copy is ever materialised;
 //   * M-tiles are runs of 128 consecutive linear pixel positions (they wrap over image rows; the 2 wrap-around
 //     columns per row are computed and discarded);
-//   * conv1: 7 M-tiles x 9 taps, N = 32, K = 16 (8 real channels + a zero chunk), accumulators in TMEM columns
+//   * conv1: per M-tile 5 tcgen05.mma, N = 32, K = 16 = two 8-channel filter taps per instruction (the second K chunk
+//     is the first one shifted by the descriptor's leading-dimension offset), accumulators in TMEM columns
 //     [32*i, 32*i+32);  epilogue 1 (tcgen05.ld -> +bias, relu6, fp16) writes the 32-channel activation back to
 //     shared memory as four 8-channel planes (again 16 B per pixel per plane), zero outside the image;
-//   * conv2: 6 M-tiles x 9 taps x 2 k-steps, N = 16 (8 real outputs), K = 16, A = two planes per k-step (LBO = plane
-//     stride); accumulators reuse the TMEM columns;  epilogue 2 -> +bias, relu6, fp16 -> fp32 softmax / guidance.
-//   * 256 TMEM columns and ~99 KB of shared memory per CTA => two CTAs per SM overlap each other's phases.
+//   * conv2: per M-tile 9 taps x 2 k-steps, N = 16 (8 real outputs), K = 16, A = two planes per k-step (LBO = plane
+//     stride); accumulators reuse TMEM columns already drained;  epilogue 2 -> +bias, relu6, fp16 -> fp32 softmax /
+//     guidance;
+//   * the M-tiles are software-pipelined through single-use mbarriers: one MMA-issuing warp, two 4-warp epilogue teams
+//     (see the kernel);  256 TMEM columns and <= 110 KB of shared memory per CTA => two CTAs per SM.
 //
-// The kernel filter (denoiser/extension/filtering.cu:108-228) then runs as ONE launch for all levels with
-// e^{g} precomputed once per pixel and level (guidance is in [0,6] after relu6, so the reference's max-subtraction
-// is not needed for range) and 4 output rows per thread sharing their taps.
+// The kernel filter (denoiser/extension/filtering.cu:108-228) then runs as ONE launch for all levels, separated into
+// a horizontal and a vertical box sum of e^{g} * (r,g,b,1) (guidance is in [0,6] after relu6, so the reference's
+// max-subtraction is not needed for range).
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -378,8 +381,8 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
                     const size_t p = (size_t)gy * W + gx;
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
-                        d.weight_map[l * HW + p] = e[l] / sum;
-                        d.guidance_map[l * HW + p] = o[4 + l];
+                        RTO_ST(d.weight_map + l * HW + p, e[l] / sum);
+                        RTO_ST(d.guidance_map + l * HW + p, o[4 + l]);
                     }
                 }
             }
@@ -392,88 +395,10 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     }
 }
 
-// ------------------------------------------------------------------------------------------------ fast filter
+// ------------------------------------------------------------------------------------------------ separable filter
 // out(p) = sum_l w_l(p) * [sum_{q in N_l(p)} E_l(q) rgb(q)] / [sum_{q in N_l(p)} E_l(q)],  E_l = exp(g_l), 0 outside the
 // image (filtering.cu:108-228 with exp(g - max)/sum == exp(g)/sum; valid because relu6 bounds g to [0,6]).
-namespace ff {
-constexpr int BW = 32, BH = 32, R = 4, TWD = BW + 2 * R, THT = BH + 2 * R;   // 40 x 40 staged tile
-constexpr int ROWS = 4;                                                       // output rows per thread
-constexpr int THREADS = BW * (BH / ROWS);                                     // 256
-constexpr int SMEM_BYTES = TWD * THT * (16 + 4 * 4);
-}  // namespace ff
-
-__global__ void __launch_bounds__(ff::THREADS) filter_fast_kernel(const float* __restrict__ aux, const float* __restrict__ weight,
-                                                                 const float* __restrict__ guidance, int W, int H, int y0,
-                                                                 int y1, float4* __restrict__ out) {
-    using namespace ff;
-    extern __shared__ __align__(16) unsigned char fsm[];
-    float4* rgb = reinterpret_cast<float4*>(fsm);                 // [THT][TWD] (r,g,b,unused)
-    float* E = reinterpret_cast<float*>(fsm + TWD * THT * 16);   // [4][THT][TWD]
-    const int tid = threadIdx.x;
-    const int bx = blockIdx.x * BW, by = y0 + blockIdx.y * BH;
-    const size_t HW = (size_t)W * H;
-    for (int i = tid; i < TWD * THT; i += THREADS) {
-        const int x = i % TWD, y = i / TWD;
-        const int gx = bx + x - R, gy = by + y - R;
-        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-            const size_t p = (size_t)gy * W + gx;
-            c = make_float4(__ldg(aux + p), __ldg(aux + HW + p), __ldg(aux + 2 * HW + p), 0.f);
-            e0 = __expf(__ldg(guidance + p));
-            e1 = __expf(__ldg(guidance + HW + p));
-            e2 = __expf(__ldg(guidance + 2 * HW + p));
-            e3 = __expf(__ldg(guidance + 3 * HW + p));
-        }
-        rgb[i] = c;
-        E[i] = e0; E[TWD * THT + i] = e1; E[2 * TWD * THT + i] = e2; E[3 * TWD * THT + i] = e3;
-    }
-    __syncthreads();
-    const int tx = tid % BW, ty = (tid / BW) * ROWS;
-    const int gx = bx + tx;
-    float o[ROWS][3];
-#pragma unroll
-    for (int k = 0; k < ROWS; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const int S = l + 1;
-        const float* El = E + l * TWD * THT;
-        float acc[ROWS][4];
-#pragma unroll
-        for (int k = 0; k < ROWS; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
-        // tap rows ry (relative to output row ty) from -S to ROWS-1+S ; row ry feeds outputs k with |ry - k| <= S
-#pragma unroll
-        for (int ry = -S; ry <= ROWS - 1 + S; ++ry) {
-            const int base = (ty + R + ry) * TWD + tx + R;
-#pragma unroll
-            for (int dx = -S; dx <= S; ++dx) {
-                const float e = El[base + dx];
-                const float4 c = rgb[base + dx];
-                const float er = e * c.x, eg = e * c.y, eb = e * c.z;
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k)
-                    if (ry - k >= -S && ry - k <= S) { acc[k][0] += er; acc[k][1] += eg; acc[k][2] += eb; acc[k][3] += e; }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < ROWS; ++k) {
-            const int gy = by + ty + k;
-            if (gx < W && gy < H && gy < y1) {
-                const float w = __ldg(weight + l * HW + (size_t)gy * W + gx) * (1.0f / acc[k][3]);
-                o[k][0] += acc[k][0] * w; o[k][1] += acc[k][1] * w; o[k][2] += acc[k][2] * w;
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < ROWS; ++k) {
-        const int gy = by + ty + k;
-        if (gx < W && gy < H && gy < y1) out[(size_t)gy * W + gx] = make_float4(o[k][0], o[k][1], o[k][2], 1.0f);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ separable filter
-// The same sums as filter_fast_kernel, but sum_{q in N_l(p)} E_l(q) (rgb(q),1) is a BOX sum of the premultiplied field
-// E_l*(r,g,b,1), so it separates: a horizontal pass (registers, inputs straight from global/L2, 4 adjacent outputs per
+// sum_{q in N_l(p)} E_l(q) (rgb(q),1) is a BOX sum of the premultiplied field E_l*(r,g,b,1), so it separates: a horizontal pass (registers, inputs straight from global/L2, 4 adjacent outputs per
 // thread) writes H_l[row][col] to shared memory, a vertical pass adds 2S+1 rows of H_l.  Work per pixel drops from
 // 164 taps x 4 FMA to 24 x 4 FMA (x 32/24 halo rows) + 24 x 4 FADD.  Summation order differs from the exact kernel
 // (fp32, <= 81 positive terms: relative 1e-6), well inside the 1e-3 image tolerance; rto_filter keeps the exact kernel.
@@ -490,11 +415,11 @@ __device__ __forceinline__ void load12(const float* __restrict__ plane, int W, b
     for (int s = 0; s < 3; ++s) {
         const int x = xs + 4 * s;
         if (rowin && vec && x >= 0 && x + 3 < W) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(plane + rowoff + x));
+            const float4 t = RTO_LD_LAST(reinterpret_cast<const float4*>(plane + rowoff + x));
             v[4 * s] = t.x; v[4 * s + 1] = t.y; v[4 * s + 2] = t.z; v[4 * s + 3] = t.w;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[4 * s + k] = (rowin && x + k >= 0 && x + k < W) ? __ldg(plane + rowoff + x + k) : 0.f;
+            for (int k = 0; k < 4; ++k) v[4 * s + k] = (rowin && x + k >= 0 && x + k < W) ? RTO_LD_LAST(plane + rowoff + x + k) : 0.f;
         }
     }
 }
@@ -564,7 +489,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
             for (int k = 0; k < 3; ++k) {
                 const int gy = by + ty + k;
                 if (gx < W && gy < H && gy < y1) {
-                    const float w = __ldg(weight + l * HW + (size_t)gy * W + gx) * (1.0f / acc[k].w);
+                    const float w = RTO_LD_LAST(weight + l * HW + (size_t)gy * W + gx) * (1.0f / acc[k].w);
                     o[k][0] += acc[k].x * w; o[k][1] += acc[k].y * w; o[k][2] += acc[k].z * w;
                 }
             }
@@ -572,7 +497,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int gy = by + ty + k;
-            if (gx < W && gy < H && gy < y1) out[(size_t)gy * W + gx] = make_float4(o[k][0], o[k][1], o[k][2], 1.0f);
+            if (gx < W && gy < H && gy < y1) RTO_ST(out + (size_t)gy * W + gx, make_float4(o[k][0], o[k][1], o[k][2], 1.0f));
         }
     }
 }
@@ -624,21 +549,14 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
                                float4* out, cudaStream_t stream) {
     const int rows = y1 - y0;
     if (rows <= 0) return cudaSuccess;
-    static int impl = -1;   // RTO_FILTER_IMPL=taps selects the direct 164-tap kernel (A/B and debugging)
-    if (impl < 0) {
-        const char* v = getenv("RTO_FILTER_IMPL");
-        impl = (v && v[0] == 't') ? 1 : 0;
-        cudaError_t e = cudaFuncSetAttribute(filter_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ff::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(filter_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs::SMEM_BYTES);
-        if (e != cudaSuccess) { impl = -1; return e; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(filter_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
     }
-    if (impl == 1) {
-        dim3 grid((W + ff::BW - 1) / ff::BW, (rows + ff::BH - 1) / ff::BH);
-        filter_fast_kernel<<<grid, ff::THREADS, ff::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
-    } else {
-        dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
-        filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
-    }
+    dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
+    filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,17 @@
 
 #include "rto_ray.cuh"
 
+// Cache hints for the per-frame streaming buffers (aux, maps, image): written once and read once per frame, they should
+// not displace the tree's brick grid from L2.  st.global.cs / ld.global.cs mark the lines evict-first.
+// (B200, bench workload, 4 frames in flight: +0.8 % frames/s; with the L2 persistence window over the bricks +3 %.)
+#ifndef RTO_NO_STREAM_HINTS
+#define RTO_ST(p, v) __stcs((p), (v))
+#define RTO_LD_LAST(p) __ldcs(p)
+#else
+#define RTO_ST(p, v) (*(p) = (v))
+#define RTO_LD_LAST(p) __ldg(p)
+#endif
+
 namespace rto {
 
 // HBM layout of a loaded tree (structure of arrays)

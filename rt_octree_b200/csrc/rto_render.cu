@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             if (a.aux) {
                 const size_t SIZE = (size_t)fp.W * fp.H;
                 float* q = a.aux + idx;
-                q[0] = out0; q[SIZE] = out1; q[2 * SIZE] = out2; q[3 * SIZE] = out3;
-                q[4 * SIZE] = f_mul(out0, out0); q[5 * SIZE] = f_mul(out1, out1);
-                q[6 * SIZE] = f_mul(out2, out2); q[7 * SIZE] = f_mul(out3, out3);
+                RTO_ST(q, out0); RTO_ST(q + SIZE, out1); RTO_ST(q + 2 * SIZE, out2); RTO_ST(q + 3 * SIZE, out3);
+                RTO_ST(q + 4 * SIZE, f_mul(out0, out0)); RTO_ST(q + 5 * SIZE, f_mul(out1, out1));
+                RTO_ST(q + 6 * SIZE, f_mul(out2, out2)); RTO_ST(q + 7 * SIZE, f_mul(out3, out3));
             }
-            if (a.img) a.img[idx] = make_float4(out0, out1, out2, 1.0f);
+            if (a.img) RTO_ST(a.img + idx, make_float4(out0, out1, out2, 1.0f));
         }
         __syncwarp();
     }
@@ -282,12 +282,12 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
     int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;
-    // Optional L2 persistence window over the brick array (RTO_L2_PERSIST=1): keeps the grid resident in the 126 MB L2
-    // while the per-frame buffers (aux, maps, image) stream through.
+    // L2 persistence window over the brick array (RTO_L2_PERSIST=0 turns it off): keeps as much of the grid as the
+    // device allows resident in the 126 MB L2 while the per-frame buffers (aux, maps, image) stream through.
     static int persist = -1;
     if (persist < 0) {
         const char* e = getenv("RTO_L2_PERSIST");
-        persist = (e && e[0] == '1') ? 1 : 0;
+        persist = (e && e[0] == '0') ? 0 : 1;
         if (persist) {
             int dev = 0, max_persist = 0;
             cudaGetDevice(&dev);

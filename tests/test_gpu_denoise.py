@@ -165,8 +165,8 @@ def test_denoise_end_to_end(capi, oracle, mid_tree, poses8, net_weights, impl):
 @pytest.mark.parametrize("shape", [(67, 129), (5, 7), (33, 31), (24, 32), (25, 36), (152, 200), (97, 258)])
 def test_denoise_stored_buffer_odd_sizes(capi, oracle, net_weights, shape):
     """Production denoiser (tcgen05 net + separable filter) on an uploaded guidance buffer at ragged sizes
-    (W % 4 != 0 exercises the scalar-load path, H % 24 / W % 32 the partial tiles) against the oracle, plus the direct
-    164-tap kernel (RTO_FILTER_IMPL is read once per process, so the A/B runs through the exact rto_filter)."""
+    (W % 4 != 0 exercises the scalar-load paths, H % 24 / W % 32 the partial tiles) against the oracle, and against the
+    exact 164-tap rto_filter on the same maps (isolates the separable filter's summation-order error)."""
     import torch
 
     H, W = shape

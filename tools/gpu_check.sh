@@ -38,7 +38,7 @@ if has ncu; then
       python bench.py --steps 12 --warmup 3 --no-baselines > gpurun_out/ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 6 -c 2 -f -o gpurun_out/prof_render \
       python bench.py --steps 12 --warmup 3 --no-baselines > gpurun_out/ncu_render.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"guidance_net|filter_fast|filter_kernel" -s 6 -c 2 -f -o gpurun_out/prof_denoise \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"guidance_net|filter_sep|filter_kernel" -s 6 -c 2 -f -o gpurun_out/prof_denoise \
       python bench.py --steps 12 --warmup 3 --no-baselines > gpurun_out/ncu_denoise.log 2>&1
   ls -la gpurun_out
 fi

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
 }
 
 // Resident blocks per SM of the persistent kernel.  More warps raise issue utilisation but every warp then advances
-// more slowly, and the frame time is bounded below by the LONGEST ray's serial chain (DESIGN.md §4.3), so the optimum
+// more slowly, and the frame time is bounded below by the LONGEST ray's serial chain (DESIGN.md §4.4), so the optimum
 // is well below the occupancy limit.  RTO_RENDER_BLOCKS_PER_SM overrides the default for tuning.
 static int tuned_blocks_per_sm(int occ_limit) {
     static int env = -1;

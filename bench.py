@@ -85,7 +85,6 @@ class ClockSampler:
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
         self.p.terminate()
         sm, smax, reasons = [], [], set()
         for r in self.rows:
@@ -307,7 +306,6 @@ def run_cuda_arm(args):
     torch.cuda.synchronize()
     launches = capi.launch_count() - launches0
     ms_total = max(e0.elapsed_time(e) for e in ends)
-    clk = clocks.stop() if rank == 0 else None
     barrier()
 
     # ---- per-kernel stage times (Timer: cudaEvents around each launch), same frames
@@ -357,6 +355,9 @@ def run_cuda_arm(args):
         e2e_frame(i, f)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # clocks / throttle reasons were sampled (nvidia-smi, 100 ms period) from the start of the device-timed loop to here:
+    # the timed region itself can be shorter than one sampling period, the loops after it keep the GPU under the same load
+    clk = clocks.stop() if rank == 0 else None
     checksum = float(pinned[(K - 1) % NBUF].sum())
 
     # ---- reduce over ranks: max time

@@ -377,11 +377,12 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
                     const float mx = fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3]));
                     float e[4], sum = 0.f;
 #pragma unroll
-                    for (int l = 0; l < 4; ++l) { e[l] = expf(o[l] - mx); sum += e[l]; }
+                    for (int l = 0; l < 4; ++l) { e[l] = __expf(o[l] - mx); sum += e[l]; }
+                    const float inv = __fdividef(1.0f, sum);   // logits are fp16 values in [0,6]: one fp16 ulp moves a weight by 4e-3
                     const size_t p = (size_t)gy * W + gx;
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
-                        RTO_ST(d.weight_map + l * HW + p, e[l] / sum);
+                        RTO_ST(d.weight_map + l * HW + p, e[l] * inv);
                         RTO_ST(d.guidance_map + l * HW + p, o[4 + l]);
                     }
                 }
@@ -409,17 +410,57 @@ constexpr int SMEM_BYTES = 4 * SROWS * BW * 16;                    // H[4][32][3
 static_assert(SROWS * (BW / 4) == THREADS && BW * (BH / 3) == THREADS, "thread mapping");
 }  // namespace fs
 
+// 12 consecutive pixels of one plane row starting at xs (xs % 4 == 0).  GUARD = false: the CTA's whole halo is inside the
+// image and rows are 16-byte aligned, so no bounds logic at all (the case for all but the border tiles).
+template <bool GUARD>
 __device__ __forceinline__ void load12(const float* __restrict__ plane, int W, bool vec, bool rowin, size_t rowoff, int xs,
                                        float (&v)[12]) {
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
         const int x = xs + 4 * s;
-        if (rowin && vec && x >= 0 && x + 3 < W) {
+        if (!GUARD || (rowin && vec && x >= 0 && x + 3 < W)) {
             const float4 t = RTO_LD_LAST(reinterpret_cast<const float4*>(plane + rowoff + x));
             v[4 * s] = t.x; v[4 * s + 1] = t.y; v[4 * s + 2] = t.z; v[4 * s + 3] = t.w;
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[4 * s + k] = (rowin && x + k >= 0 && x + k < W) ? RTO_LD_LAST(plane + rowoff + x + k) : 0.f;
+        }
+    }
+}
+
+// pass 1: horizontal sums of E_l * (r,g,b,1) for staged row r, outputs x = bx + 4*xg + j
+template <bool GUARD>
+__device__ __forceinline__ void filter_pass1(const float* __restrict__ aux, const float* __restrict__ guidance, int W, int H,
+                                             int bx, int by, int tid, float4* __restrict__ Hs) {
+    using namespace fs;
+    const size_t HW = (size_t)W * H;
+    const bool vec = (W & 3) == 0;                                // planes and rows 16-byte aligned
+    const int r = tid >> 3, xg = tid & 7;
+    const int gy = by + r - R;
+    const int xs = bx + 4 * xg - R;
+    const bool rowin = !GUARD || (gy >= 0 && gy < H);
+    const size_t rowoff = rowin ? (size_t)gy * W : 0;
+    float cr[12], cg[12], cb[12];
+    load12<GUARD>(aux, W, vec, rowin, rowoff, xs, cr);
+    load12<GUARD>(aux + HW, W, vec, rowin, rowoff, xs, cg);
+    load12<GUARD>(aux + 2 * HW, W, vec, rowin, rowoff, xs, cb);
+    const int sw = (xg >> 1) & 3;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const int S = l + 1;
+        float e[12];
+        load12<GUARD>(guidance + l * HW, W, vec, rowin, rowoff, xs, e);
+#pragma unroll
+        for (int i = R - S; i <= R + 3 + S; ++i) e[i] = (!GUARD || (rowin && xs + i >= 0 && xs + i < W)) ? __expf(e[i]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int dx = -S; dx <= S; ++dx) {
+                const int i = R + j + dx;
+                a.x = fmaf(e[i], cr[i], a.x); a.y = fmaf(e[i], cg[i], a.y); a.z = fmaf(e[i], cb[i], a.z); a.w += e[i];
+            }
+            Hs[(l * SROWS + r) * BW + 4 * xg + (j ^ sw)] = a;   // swizzle: conflict-free 16-byte stores
         }
     }
 }
@@ -433,37 +474,10 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
     const int tid = threadIdx.x;
     const int bx = blockIdx.x * BW, by = y0 + blockIdx.y * BH;
     const size_t HW = (size_t)W * H;
-    const bool vec = (W & 3) == 0;                                // planes and rows 16-byte aligned
-    {   // ---- pass 1: horizontal sums of E_l * (r,g,b,1) for staged row r, outputs x = bx + 4*xg + j
-        const int r = tid >> 3, xg = tid & 7;
-        const int gy = by + r - R;
-        const int xs = bx + 4 * xg - R;
-        const bool rowin = gy >= 0 && gy < H;
-        const size_t rowoff = rowin ? (size_t)gy * W : 0;
-        float cr[12], cg[12], cb[12];
-        load12(aux, W, vec, rowin, rowoff, xs, cr);
-        load12(aux + HW, W, vec, rowin, rowoff, xs, cg);
-        load12(aux + 2 * HW, W, vec, rowin, rowoff, xs, cb);
-        const int sw = (xg >> 1) & 3;
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const int S = l + 1;
-            float e[12];
-            load12(guidance + l * HW, W, vec, rowin, rowoff, xs, e);
-#pragma unroll
-            for (int i = 0; i < 12; ++i) e[i] = (rowin && xs + i >= 0 && xs + i < W) ? __expf(e[i]) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int dx = -S; dx <= S; ++dx) {
-                    const int i = R + j + dx;
-                    a.x = fmaf(e[i], cr[i], a.x); a.y = fmaf(e[i], cg[i], a.y); a.z = fmaf(e[i], cb[i], a.z); a.w += e[i];
-                }
-                Hs[(l * SROWS + r) * BW + 4 * xg + (j ^ sw)] = a;   // swizzle: conflict-free 16-byte stores
-            }
-        }
-    }
+    const bool interior = (W & 3) == 0 && bx >= R && bx + BW + R <= W && by >= R && by + BH + R <= H &&
+                          (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && (reinterpret_cast<uintptr_t>(guidance) & 15) == 0;
+    if (interior) filter_pass1<false>(aux, guidance, W, H, bx, by, tid, Hs);
+    else filter_pass1<true>(aux, guidance, W, H, bx, by, tid, Hs);
     __syncthreads();
     {   // ---- pass 2: vertical sums, weights, output
         const int x = tid & 31, ty = (tid >> 5) * 3;
@@ -489,7 +503,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
             for (int k = 0; k < 3; ++k) {
                 const int gy = by + ty + k;
                 if (gx < W && gy < H && gy < y1) {
-                    const float w = RTO_LD_LAST(weight + l * HW + (size_t)gy * W + gx) * (1.0f / acc[k].w);
+                    const float w = __fdividef(RTO_LD_LAST(weight + l * HW + (size_t)gy * W + gx), acc[k].w);
                     o[k][0] += acc[k].x * w; o[k][1] += acc[k].y * w; o[k][2] += acc[k].z * w;
                 }
             }

@@ -2,7 +2,7 @@
 //
 // The two 3x3 convolutions of the deployed GuidanceNet (denoiser/network.py:123-168: conv 8->32, relu6, conv 32->8,
 // relu6, fp16 storage / fp32 accumulate) are the only dense contraction on the render path.  The reference runs
-// them through libtorch/cuDNN (src/denoiser/denoiser.cpp:46).  Here each CTA owns a 60 x TH pixel tile (TH = 10/12/14) and
+// them through libtorch/cuDNN (src/denoiser/denoiser.cpp:46).  Here each CTA owns a 60 x TH pixel tile (TH = 10) and
 // runs both convolutions as implicit GEMMs with M = pixels:
 //
 //   * the tile (+2 px halo) is staged in shared memory PIXEL-MAJOR with a pitch of 64 pixels, 8 fp16 channels =
@@ -62,6 +62,7 @@ struct Cfg {
     static constexpr int SMEM_BYTES = OFF_TMEM + 8;
     static_assert(N1_TILES * 32 <= TMEM_COLS, "conv1 accumulators must fit the TMEM allocation");
     static_assert(128 * N1_TILES + 129 < IN_PX && 128 * N2_TILES + 194 < MID_PX, "operand reads stay inside the buffers");
+    static constexpr int TMEM_ALLOC = N1_TILES * 32 <= 128 ? 128 : 256;    // columns allocated (power of two)
     static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
 };
 
@@ -203,7 +204,7 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
 
     // ---- one-time setup: TMEM allocation (warp 0), mbarriers (one thread)
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_base + C::OFF_TMEM), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_base + C::OFF_TMEM), "n"(C::TMEM_ALLOC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 32) {
@@ -392,7 +393,7 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(C::TMEM_ALLOC) : "memory");
     }
 }
 
@@ -529,33 +530,23 @@ static cudaError_t launch_net_th(const NetDev& net, const void* packed, const De
     return cudaGetLastError();
 }
 
-// Tile height: two CTAs are resident per SM (TMEM: 2 x 256 columns), so the launch runs in ceil(tiles / (2 * SMs)) rounds
-// of cost ~ (TH + 4) staged rows each; pick the height with the cheapest total (800 rows: 14 -> 3 rounds, 12 -> 4 rounds).
+// Tile height.  Measured on B200 with four frames in flight (bench workload): TH 8 / 10 / 12 -> 4747 / 4760 / 4715 frames/s,
+// TH 14 -> 4197: the kernel's own time is the same (45 us) for all of them, but at TH = 14 two CTAs take 218 KB of
+// shared memory per SM and nothing of the neighbouring frames' kernels can be co-resident.  RTO_NET_TILE_H overrides.
 cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream) {
     const int rows = d.y1 - d.y0;
     if (rows <= 0) return cudaSuccess;
-    static int num_sms = 0, forced = -1;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
+    static int th = 0;
+    if (th == 0) {
         const char* v = getenv("RTO_NET_TILE_H");
-        forced = v ? atoi(v) : 0;
+        th = v ? atoi(v) : 10;
+        if (th != 8 && th != 10 && th != 12 && th != 14) th = 10;
     }
-    const int cols = (d.W + tc::TW - 1) / tc::TW;
-    int best = 12;
-    long best_cost = -1;
-    for (int th : {14, 12, 10}) {
-        const long tiles = (long)cols * ((rows + th - 1) / th);
-        const long cost = ((tiles + 2 * num_sms - 1) / (2 * num_sms)) * (th + 4);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = th; }
-    }
-    if (forced == 10 || forced == 12 || forced == 14) best = forced;
-    switch (best) {
+    switch (th) {
+        case 8: return launch_net_th<8>(net, packed, d, rows, stream);
+        case 12: return launch_net_th<12>(net, packed, d, rows, stream);
         case 14: return launch_net_th<14>(net, packed, d, rows, stream);
-        case 10: return launch_net_th<10>(net, packed, d, rows, stream);
-        default: return launch_net_th<12>(net, packed, d, rows, stream);
+        default: return launch_net_th<10>(net, packed, d, rows, stream);
     }
 }
 

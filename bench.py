@@ -285,13 +285,13 @@ def run_cuda_arm(args):
     #      issued alternately on two (context, stream) pairs: the long tail of one frame's render kernel (a few heavy
     #      warps) overlaps the next frame's start.  --serial uses one stream (the reference's protocol).
     n_pipe = 1 if args.serial else args.pipe
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()     # before the warm-up so that nvidia-smi is already streaming when the timed region starts
     for i in range(Wm):
         frame(ctxs[i % n_pipe], my_frames[i % K], streams[i % n_pipe].cuda_stream)
     torch.cuda.synchronize()
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     e0 = torch.cuda.Event(enable_timing=True)
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_pipe)]
     launches0 = capi.launch_count()

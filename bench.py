@@ -355,16 +355,37 @@ def run_cuda_arm(args):
         e2e_frame(i, f)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # same loop with the RGBA8 readback (the bytes the CLI writes to PNG; a quarter of the D2H traffic) - reported beside e2e
+    pinned8 = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
+
+    def e2e8_frame(i, f):
+        c, st = ctxs[i % NBUF], streams[i % NBUF]
+        st.synchronize()
+        cam.transform = host_poses[f % len(poses)]
+        c.rng_set_frame(f, WARMUP_RNG)
+        capi.launch_renderer(tree_h, cam, opt, c, stream=st.cuda_stream)
+        net.denoise(cam, c, stream=st.cuda_stream)
+        c.read_image_rgba8(pinned8[i % NBUF].numpy(), stream=st.cuda_stream, sync=False)
+
+    for i in range(NBUF):
+        e2e8_frame(i, my_frames[i % K])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i, f in enumerate(my_frames):
+        e2e8_frame(i, f)
+    torch.cuda.synchronize()
+    e2e8_s = time.perf_counter() - t0
     # clocks / throttle reasons were sampled (nvidia-smi, 100 ms period) from the start of the device-timed loop to here:
     # the timed region itself can be shorter than one sampling period, the loops after it keep the GPU under the same load
     clk = clocks.stop() if rank == 0 else None
     checksum = float(pinned[(K - 1) % NBUF].sum())
 
     # ---- reduce over ranks: max time
-    tt = torch.tensor([ms_total, e2e_s * 1e3, cold_ms, stage_ms[0], stage_ms[1] + stage_ms[2]], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([ms_total, e2e_s * 1e3, cold_ms, stage_ms[0], stage_ms[1] + stage_ms[2], e2e8_s * 1e3], device="cuda",
+                      dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, cold_ms, render_ms, denoise_ms = [float(v) for v in tt.cpu()]
+    ms_total, e2e_ms, cold_ms, render_ms, denoise_ms, e2e8_ms = [float(v) for v in tt.cpu()]
     if rank == 0:
         bytes_frame, counters = algorithmic_bytes(capi, tree_h, ctx, cam, opt, poses, my_frames[: min(K, 8)])
         peaks = {}
@@ -396,6 +417,8 @@ def run_cuda_arm(args):
             "stage_ms": {"render": render_ms, "denoise": denoise_ms},
             "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 48 + 28,
                     "d2h_bytes_per_step": W * H * 16, "checksum": checksum},
+            "e2e_rgba8": {"value": world * K / (e2e8_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": W * H * 4,
+                          "note": "same loop, image read back as RGBA8 (rto_context_read_image_rgba8: the bytes the CLI writes to PNG)"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "render_kernel<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",

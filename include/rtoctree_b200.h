@@ -134,6 +134,9 @@ int rto_context_read_aux(rto_context* ctx, float* host_dst, void* stream);
  * same layout) so that rto_denoise can run on it without rendering */
 int rto_context_write_aux(rto_context* ctx, const float* host_src, void* stream);
 int rto_context_read_image(rto_context* ctx, float* host_dst, void* stream);
+/* the same image as RGBA8 [H][W][4], converted on the device exactly like the reference CLI converts on the host before
+ * writing a PNG, `(uint8_t)(v * 255)` (main_headless.cpp:524-541): a quarter of the device->host bytes */
+int rto_context_read_image_rgba8(rto_context* ctx, unsigned char* host_dst, void* stream);
 
 /* ---- render : volrend::launch_renderer(tree, cam, options, ctx, stream, offscreen=true)
  *               include/volrend/cuda/renderer_kernel.hpp:11-16, src/cuda/volrend.cu:236-285 ---- */

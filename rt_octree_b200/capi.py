@@ -53,7 +53,7 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_last_error", "rto_abi_version", "rto_set_device", "rto_device_count", "rto_synchronize", "rto_render_options_default",
     "rto_tree_create", "rto_tree_set_ndc", "rto_tree_get_info", "rto_tree_destroy",
     "rto_context_create", "rto_context_destroy", "rto_context_aux", "rto_context_image", "rto_context_rng_seed",
-    "rto_context_rng_advance", "rto_context_rng_set_frame", "rto_context_rng_get", "rto_context_read_aux", "rto_context_write_aux",
+    "rto_context_rng_advance", "rto_context_rng_set_frame", "rto_context_rng_get", "rto_context_read_aux", "rto_context_write_aux", "rto_context_read_image_rgba8",
     "rto_context_read_image", "rto_render", "rto_render_rect", "rto_render_trace",
     "rto_net_create", "rto_net_destroy", "rto_net_set_impl", "rto_net_set_bias_mode", "rto_denoise", "rto_denoise_rows", "rto_net_forward",
     "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
@@ -97,6 +97,7 @@ def load(path: str = LIB_PATH):
     L.rto_context_rng_get.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rto_context_read_aux.argtypes = [P, P, P]
     L.rto_context_write_aux.argtypes = [P, P, P]
+    L.rto_context_read_image_rgba8.argtypes = [P, P, P]
     L.rto_context_read_image.argtypes = [P, P, P]
     L.rto_render.argtypes = [P, P, C.POINTER(CameraPOD), C.POINTER(RenderOptionsPOD), P]
     L.rto_render_rect.argtypes = [P, P, C.POINTER(CameraPOD), C.POINTER(RenderOptionsPOD), I, I, I, I, P]
@@ -332,6 +333,15 @@ class RenderContext:
         if host is None:
             host = np.empty((8, self.height, self.width), np.float32)
         _check(load().rto_context_read_aux(self._h, host.ctypes.data, C.c_void_p(stream)))
+        if sync:
+            _cuda_sync()
+        return host
+
+    def read_image_rgba8(self, host: np.ndarray = None, stream=0, sync=True) -> np.ndarray:
+        """Final image as uint8 [H][W][4], `(uint8)(v * 255)` on the device (the bytes the reference CLI writes to PNG)."""
+        if host is None:
+            host = np.empty((self.height, self.width, 4), np.uint8)
+        _check(load().rto_context_read_image_rgba8(self._h, host.ctypes.data, C.c_void_p(stream)))
         if sync:
             _cuda_sync()
         return host

@@ -41,6 +41,7 @@ struct rto_context {
     int W = 0, H = 0;
     float* aux = nullptr;
     float4* img = nullptr;
+    uchar4* img8 = nullptr;         // RGBA8 copy of img, allocated on first rto_context_read_image_rgba8
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
     int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
@@ -300,7 +301,7 @@ int rto_context_create(rto_context** out, int W, int H) {
 }
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
-    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
+    cudaFree(c->aux); cudaFree(c->img); cudaFree(c->img8); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
         if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
@@ -344,6 +345,16 @@ int rto_context_write_aux(rto_context* c, const float* src, void* stream) {
 int rto_context_read_image(rto_context* c, float* dst, void* stream) {
     if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
     RTO_CUDA(cudaMemcpyAsync(dst, c->img, (size_t)c->W * c->H * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RTO_OK;
+}
+int rto_context_read_image_rgba8(rto_context* c, unsigned char* dst, void* stream) {
+    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    const size_t n = (size_t)c->W * c->H;
+    if (!c->img8) RTO_CUDA(cudaMalloc(&c->img8, n * sizeof(uchar4)));
+    cudaError_t e = rto::launch_rgba8(c->img, c->img8, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "rgba8 launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    RTO_CUDA(cudaMemcpyAsync(dst, c->img8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return RTO_OK;
 }
 

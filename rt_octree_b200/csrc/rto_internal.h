@@ -90,6 +90,7 @@ cudaError_t launch_filter_simt(const float* rgb, size_t chan_stride, int pix_str
                                const float* guidance, int L, int W, int H, int y0, int y1, float4* out,
                                cudaStream_t stream, float4* save_rgb = nullptr, float* save_max = nullptr,
                                float* save_inv = nullptr);
+cudaError_t launch_rgba8(const float4* img, uchar4* out, size_t n, cudaStream_t stream);
 cudaError_t launch_filter_backward(const float* dout, const float* img_in, const float* weight, const float* guidance,
                                    const float* rgb_f, const float* max_map, const float* inv_sum, int L, int W, int H,
                                    float* grad_weight, float* grad_guidance, cudaStream_t stream);

@@ -294,10 +294,9 @@ void run_shard(const Job& job, int device, size_t begin, size_t end, float* ms, 
             std::ofstream out(job.out_dir + "/buf_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
             out.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)(buf.size() * sizeof(float)));
         } else {                  // main_headless.cpp:524-541
-            rto_check(rto_context_read_image(ctx.handle, buf.data(), stream), "read image");
+            std::vector<uint8_t> u8((size_t)4 * job.width * job.height);   // (uint8_t)(v * 255) on the device, as the reference does on the host
+            rto_check(rto_context_read_image_rgba8(ctx.handle, u8.data(), stream), "read image");
             rto_check(rto_synchronize(stream), "sync");
-            std::vector<uint8_t> u8((size_t)4 * job.width * job.height);
-            for (size_t j = 0; j < u8.size(); ++j) u8[j] = (uint8_t)(buf[j] * 255);   // truncation, no clamp — as the reference
             write_png_file(job.out_dir + "/" + job.basenames[i] + ".png", u8.data(), job.width, job.height);
         }
         if (job.write_float) {

@@ -195,6 +195,24 @@ def test_denoise_stored_buffer_odd_sizes(capi, oracle, net_weights, shape):
     assert np.abs(img - out.cpu().numpy()).max() < 5e-6
 
 
+def test_read_image_rgba8_matches_reference_conversion(capi, net_weights):
+    """RGBA8 readback == the reference CLI's host conversion `(uint8_t)(v * 255)` (main_headless.cpp:534-537) of the
+    float image, byte for byte."""
+    H, W = 97, 130
+    rs = np.random.default_rng(5)
+    aux = rs.uniform(0, 1, (8, H, W)).astype(np.float32)
+    aux[4:] = aux[:4] ** 2
+    ctx = capi.RenderContext(W, H)
+    ctx.write_aux(aux)
+    net = capi.Denoiser(net_weights)
+    net.denoise(capi.Camera(W, H, 100.0, 100.0), ctx)
+    img = ctx.read_image()
+    u8 = ctx.read_image_rgba8()
+    want = (img * np.float32(255)).astype(np.int32).astype(np.uint8)
+    assert u8.shape == (H, W, 4) and np.array_equal(u8, want)
+    assert np.all(u8[..., 3] == 255)
+
+
 def test_timer_report(capi, mid_tree, poses8, net_weights):
     from rt_octree_b200 import synthetic as S
 

@@ -57,13 +57,14 @@ struct Cfg {
     static constexpr int OFF_W2 = OFF_W1 + 9 * 512;
     static constexpr int OFF_ZERO = OFF_W2 + 9 * 1024;                      // zero block: must lie ABOVE every operand start address
     static constexpr int OFF_BIAS = OFF_ZERO + 2048;
-    static constexpr int OFF_BAR = OFF_BIAS + 40 * 4;                       // mbarriers: c1[N1] | mid[N1] | c2[N2]
-    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES);
+    static constexpr int OFF_BAR = OFF_BIAS + 40 * 4;                       // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES + 1);
     static constexpr int SMEM_BYTES = OFF_TMEM + 8;
     static_assert(N1_TILES * 32 <= TMEM_COLS, "conv1 accumulators must fit the TMEM allocation");
     static_assert(128 * N1_TILES + 129 < IN_PX && 128 * N2_TILES + 194 < MID_PX, "operand reads stay inside the buffers");
     static constexpr int TMEM_ALLOC = N1_TILES * 32 <= 128 ? 128 : 256;    // columns allocated (power of two)
     static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
+    static_assert(OFF_W1 % 16 == 0 && OFF_BIAS % 16 == 0, "bulk-copy destinations are 16-byte aligned");
 };
 
 // packed weights in global memory: [w1: 9 taps][32 out][8 in] fp16 | [w2: 9 taps][4 chunks][16 out][8 in] fp16 |
@@ -119,6 +120,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
@@ -200,6 +206,7 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     const size_t HW = (size_t)W * H;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar_c1 = s_base + C::OFF_BAR, bar_mid = bar_c1 + 8 * C::N1_TILES, bar_c2 = bar_mid + 8 * C::N1_TILES;
+    const uint32_t bar_w = bar_c2 + 8 * C::N2_TILES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
     // ---- one-time setup: TMEM allocation (warp 0), mbarriers (one thread)
@@ -210,15 +217,15 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     if (tid == 32) {
         for (int i = 0; i < C::N1_TILES; ++i) { mbar_init(bar_c1 + 8 * i, 1); mbar_init(bar_mid + 8 * i, 128); }
         for (int j = 0; j < C::N2_TILES; ++j) mbar_init(bar_c2 + 8 * j, 1);
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        // packed weights + biases: two bulk async copies (TMA engine, no registers, no thread instructions) signalling bar_w
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_w), "n"(PK_BYTES) : "memory");
+        bulk_g2s(s_base + C::OFF_W1, packed, PK_BIAS, bar_w);
+        bulk_g2s(s_base + C::OFF_BIAS, packed + PK_BIAS, PK_BYTES - PK_BIAS, bar_w);
     }
     // ---- stage weights, zero block and the input tile (fp32 planes -> fp16, 8 channels = 16 B per pixel)
     {
-        const uint4* src = reinterpret_cast<const uint4*>(packed);
-        uint4* w = reinterpret_cast<uint4*>(smem + C::OFF_W1);
-        for (int i = tid; i < (PK_BIAS) / 16; i += THREADS) w[i] = __ldg(src + i);
-        float* bias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
-        if (tid < 40) bias[tid] = __ldg(reinterpret_cast<const float*>(packed + PK_BIAS) + tid);
         uint4* z = reinterpret_cast<uint4*>(smem + C::OFF_ZERO);
         if (tid < 128) z[tid] = make_uint4(0, 0, 0, 0);
         uint4* in = reinterpret_cast<uint4*>(smem + C::OFF_IN);
@@ -268,6 +275,7 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mbar_wait(bar_w, 0);     // weights and biases have landed (long before this point in practice)
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 8) {

@@ -130,6 +130,12 @@ def launch_count() -> int:
     return int(load().rto_launch_count())
 
 
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(load().rto_device_count(C.byref(n)))
+    return int(n.value)
+
+
 def set_device(device: int):
     _check(load().rto_set_device(device))
 

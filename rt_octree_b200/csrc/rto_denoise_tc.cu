@@ -527,11 +527,15 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 
 template <int TH>
 static cudaError_t launch_net_th(const NetDev& net, const void* packed, const DenoiseArgs& d, int rows, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(guidance_net_tc_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TH>::SMEM_BYTES);
+    static bool attr_set[kMaxDevices] = {};   // per device: the opt-in shared-memory size is a per-device function attribute
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev = dev >= 0 && dev < kMaxDevices ? dev : 0;
+    if (!attr_set[dev]) {
+        e = cudaFuncSetAttribute(guidance_net_tc_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TH>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + TH - 1) / TH);
     guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias);
@@ -562,11 +566,15 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
                                float4* out, cudaStream_t stream) {
     const int rows = y1 - y0;
     if (rows <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(filter_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs::SMEM_BYTES);
+    static bool attr_set[kMaxDevices] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev = dev >= 0 && dev < kMaxDevices ? dev : 0;
+    if (!attr_set[dev]) {
+        e = cudaFuncSetAttribute(filter_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fs::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
     filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);

@@ -20,6 +20,9 @@
 
 namespace rto {
 
+constexpr int kMaxDevices = 64;   // per-device launch state (function attributes are per device)
+
+
 // HBM layout of a loaded tree (structure of arrays)
 struct TreeDev {
     const uint32_t* nodes;  // [cap*8] node words: internal = ABSOLUTE child node id; leaf = 0x80000000 | sigma fp16 bits

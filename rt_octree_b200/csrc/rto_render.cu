@@ -263,45 +263,46 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
     const bool grid_path = !trace && a.tree.grid.K > 0;
     const int v = trace ? 1 : (grid_path ? 2 : 0);
     const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
-    static size_t smem_set[3] = {0, 0, 0};
-    static int occ_limit[3] = {0, 0, 0};
-    static int num_sms = 0;
+    // Function attributes, occupancy and the L2 set-aside are per DEVICE (the CLI drives one host thread per GPU), so the
+    // cached launch state is indexed by the current device; slots of different devices are never shared between threads.
+    struct DevState {
+        int num_sms = 0;
+        size_t smem_set[3] = {0, 0, 0};
+        int occ_limit[3] = {0, 0, 0};
+        int persist = -1, max_win = 0, max_persist = 0;
+    };
+    static DevState dev_state[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    DevState& ds = dev_state[dev >= 0 && dev < kMaxDevices ? dev : 0];
     void (*kern)(RenderArgs) = trace ? render_kernel<SPP, true, false> : (grid_path ? render_kernel<SPP, false, true> : render_kernel<SPP, false, false>);
-    if (smem > smem_set[v] || occ_limit[v] == 0) {   // first launch, or a deeper tree than any seen before
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (smem > ds.smem_set[v] || ds.occ_limit[v] == 0) {   // first launch on this device, or a deeper tree than any seen before
+        if ((e = cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int occ = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem)) != cudaSuccess) return e;
-        occ_limit[v] = occ > 0 ? occ : 1;
-        smem_set[v] = smem;
+        ds.occ_limit[v] = occ > 0 ? occ : 1;
+        ds.smem_set[v] = smem;
     }
     const int n_supers = ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
-    int grid = num_sms * tuned_blocks_per_sm(occ_limit[v]);
+    int grid = ds.num_sms * tuned_blocks_per_sm(ds.occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;
     // L2 persistence window over the brick array (RTO_L2_PERSIST=0 turns it off): keeps as much of the grid as the
     // device allows resident in the 126 MB L2 while the per-frame buffers (aux, maps, image) stream through.
-    static int persist = -1;
-    if (persist < 0) {
-        const char* e = getenv("RTO_L2_PERSIST");
-        persist = (e && e[0] == '0') ? 0 : 1;
-        if (persist) {
-            int dev = 0, max_persist = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-            if (max_persist <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) persist = 0;
+    if (ds.persist < 0) {
+        const char* ev = getenv("RTO_L2_PERSIST");
+        ds.persist = (ev && ev[0] == '0') ? 0 : 1;
+        if (ds.persist) {
+            cudaDeviceGetAttribute(&ds.max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&ds.max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            if (ds.max_persist <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ds.max_persist) != cudaSuccess) ds.persist = 0;
         }
     }
-    if (persist && grid_path && a.tree.grid_brick_bytes > 0) {
-        int dev = 0, max_win = 0, max_persist = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (ds.persist && grid_path && a.tree.grid_brick_bytes > 0) {
         size_t bytes = a.tree.grid_brick_bytes;
-        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+        if (ds.max_win > 0 && bytes > (size_t)ds.max_win) bytes = (size_t)ds.max_win;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kBlockThreads);
@@ -311,7 +312,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         at[0].id = cudaLaunchAttributeAccessPolicyWindow;
         at[0].val.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(a.tree.grid.bricks);
         at[0].val.accessPolicyWindow.num_bytes = bytes;
-        at[0].val.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
+        at[0].val.accessPolicyWindow.hitRatio = bytes <= (size_t)ds.max_persist ? 1.0f : (float)ds.max_persist / (float)bytes;
         at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = at;

@@ -187,6 +187,36 @@ def test_cli_matches_reference_cli(cli, tmp_path, mid_tree, net_weights, denoise
     assert png[:8] == b"\x89PNG\r\n\x1a\n" and len(png) > 1000
 
 
+@pytest.mark.gpu
+def test_cli_num_gpus_frame_sharding(cli, tmp_path, mid_tree, net_weights, capi):
+    """--num_gpus N (one host thread per GPU, contiguous pose shards): every frame equals the single-GPU run bit for bit.
+    Needs >= 2 visible GPUs (per-device function attributes, per-device L2 set-aside); skipped on a 1-GPU box."""
+    n = capi.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from rt_octree_b200 import synthetic as S
+
+    npz = str(tmp_path / "tree.npz")
+    S.write_tree_npz(npz, mid_tree)
+    pj = str(tmp_path / "transforms_test.json")
+    S.write_blender_json(pj, S.make_poses(8)[:6])
+    oj = str(tmp_path / "opt.json")
+    S.write_opt_json(oj, spp=6, denoise=True)
+    np.savez(str(tmp_path / "ts_latest.ts.npz"), **net_weights)
+    common = [npz, pj, "--options", oj, "--ts_module", str(tmp_path / "ts_latest.ts"), "-w", "320", "-h", "240", "--write_float"]
+    outs = {}
+    for g in (1, min(n, 4)):
+        out = str(tmp_path / ("g%d" % g))
+        r = subprocess.run([cli, *common, "-o", out, "--num_gpus", str(g)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs[g] = out
+    g = min(n, 4)
+    for i in range(6):
+        a = np.fromfile(os.path.join(outs[1], "img_r_%d.bin" % i), np.float32)
+        b = np.fromfile(os.path.join(outs[g], "img_r_%d.bin" % i), np.float32)
+        assert a.size == 240 * 320 * 4 and np.array_equal(a, b), "frame %d differs between 1 and %d GPUs" % (i, g)
+
+
 def _llff_dataset(root, n=5):
     from rt_octree_b200 import synthetic as S
 

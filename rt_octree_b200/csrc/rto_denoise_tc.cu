@@ -47,29 +47,31 @@ struct Cfg {
     static constexpr int IN_PX = (TH + 4) * PW + 64;                       // staged input pixels (+ slack read only by discarded rows)
     static constexpr int Q1_MIN = PW + 1;                                  // conv1 positions: x in [1,62], y in [1,TH+2]
     static constexpr int N1_TILES = ((TH + 2) * PW - 2 + 127) / 128;
-    static constexpr int Q2_MIN = 2 * PW + 2;                              // conv2 positions: x in [2,61], y in [2,TH+1]
-    static constexpr int N2_TILES = (TH * PW - 4 + 127) / 128;
+    static constexpr int Q2_MIN = 2 * PW;                                  // conv2 M-tile j = image rows y = 2+2j, 3+2j (x = 0..63)
+    static constexpr int N2_TILES = TH / 2;
     static constexpr int MID_PX = 128 * N1_TILES + 128;                    // positions per 8-channel plane of the conv1 activation
     // shared memory map (bytes)
     static constexpr int OFF_IN = 0;
     static constexpr int OFF_MID = OFF_IN + IN_PX * 16;
     static constexpr int OFF_W1 = OFF_MID + 4 * MID_PX * 16;
     static constexpr int OFF_W2 = OFF_W1 + 9 * 512;
-    static constexpr int OFF_ZERO = OFF_W2 + 9 * 1024;                      // zero block: must lie ABOVE every operand start address
+    static constexpr int OFF_ZERO = OFF_W2 + 6 * 1024;                      // zero block: must lie ABOVE every operand start address
     static constexpr int OFF_BIAS = OFF_ZERO + 2048;
-    static constexpr int OFF_BAR = OFF_BIAS + 40 * 4;                       // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights
+    static constexpr int OFF_XCH = OFF_BIAS + 40 * 4;                       // epilogue-2 neighbour exchange: [team][parity][pair][dir][8] floats
+    static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 2 * 2 * 32;            // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES + 1);
     static constexpr int SMEM_BYTES = OFF_TMEM + 8;
     static_assert(N1_TILES * 32 <= TMEM_COLS, "conv1 accumulators must fit the TMEM allocation");
-    static_assert(128 * N1_TILES + 129 < IN_PX && 128 * N2_TILES + 194 < MID_PX, "operand reads stay inside the buffers");
+    static_assert(TH % 2 == 0 && N2_TILES <= N1_TILES, "conv2 tiles are row pairs and reuse the TMEM columns of conv1 tile j");
+    static_assert(128 * N1_TILES + 129 < IN_PX && Q2_MIN + 128 * N2_TILES + PW < MID_PX, "operand reads stay inside the buffers");
     static constexpr int TMEM_ALLOC = N1_TILES * 32 <= 128 ? 128 : 256;    // columns allocated (power of two)
     static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
     static_assert(OFF_W1 % 16 == 0 && OFF_BIAS % 16 == 0, "bulk-copy destinations are 16-byte aligned");
 };
 
-// packed weights in global memory: [w1: 9 taps][32 out][8 in] fp16 | [w2: 9 taps][4 chunks][16 out][8 in] fp16 |
-// b1 [32] fp32 | b2 [8] fp32
-constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 9 * 1024, PK_BYTES = PK_BIAS + 40 * 4;
+// packed weights in global memory: [w1: 9 taps][32 out][8 in] fp16 |
+// [w2: 3 dy][2 k-steps][2 chunks][32 rows = dx*8 + out (24 used)][8 in] fp16 | b1 [32] fp32 | b2 [8] fp32
+constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 6 * 1024, PK_BYTES = PK_BIAS + 40 * 4;
 }  // namespace tc
 
 size_t denoise_tc_packed_bytes() { return tc::PK_BYTES; }
@@ -83,16 +85,17 @@ __global__ void pack_weights_kernel(const NetDev net, unsigned char* __restrict_
         const int ci = tid % 8, co = (tid / 8) % 32, t = tid / 256;
         w1[tid] = net.w1[(co * 8 + ci) * 9 + t];
     }
-    if (tid < 9 * 4 * 16 * 8) {  // [tap][chunk][co16][ci8] <- w2[co][chunk*8+ci][tap], rows 8..15 zero
-        const int ci = tid % 8, co = (tid / 8) % 16, c = (tid / 128) % 4, t = tid / 512;
-        w2[tid] = co < 8 ? net.w2[(co * 32 + c * 8 + ci) * 9 + t] : __float2half(0.f);
+    if (tid < 3 * 2 * 2 * 32 * 8) {  // [dy][k-step s][chunk c][row n = dx*8+co][ci8] <- w2[co][(2s+c)*8+ci][dy*3+dx], rows 24..31 zero
+        const int ci = tid % 8, n = (tid / 8) % 32, c = (tid / 256) % 2, ks = (tid / 512) % 2, dy = tid / 1024;
+        const int dx = n / 8, co = n % 8;
+        w2[tid] = dx < 3 ? net.w2[(co * 32 + (2 * ks + c) * 8 + ci) * 9 + dy * 3 + dx] : __float2half(0.f);
     }
     if (tid < 32) bias[tid] = __half2float(net.b1[tid]);
     if (tid < 8) bias[32 + tid] = __half2float(net.b2[tid]);
 }
 
 cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream) {
-    pack_weights_kernel<<<(9 * 4 * 16 * 8 + 255) / 256, 256, 0, stream>>>(net, static_cast<unsigned char*>(packed_dev));
+    pack_weights_kernel<<<(3 * 2 * 2 * 32 * 8 + 255) / 256, 256, 0, stream>>>(net, static_cast<unsigned char*>(packed_dev));
     return cudaGetLastError();
 }
 
@@ -305,24 +308,25 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
                 }
                 umma_commit(bar_c1 + 8 * i);
             }
-            // ---- conv2: per M-tile 9 taps x 2 k-steps, D[128 x 16] += A[128 x 16] * B[16 x 16]^T.  Tile j reads activation
-            // positions of conv1 tiles j..j+2, and its accumulator reuses TMEM columns of conv1 tile j/2, which the
-            // epilogue has finished reading by then.
-            constexpr uint32_t idesc2 = make_idesc(16);
+            // ---- conv2: the three horizontal taps ride in N.  D'[r][dx*8+o] = sum_{dy,c} mid[r + dy*64][c] * w2[o][c][dy][dx]
+            // needs no x-shift of A, so an M-tile costs 3 dy x 2 k-steps = 6 MMAs (M128 N32 K16) instead of 18; the epilogue
+            // adds D'[r-1][dx=-1] + D'[r][dx=0] + D'[r+1][dx=+1].  M-tile j = two image rows (positions 128+128j ..), so both of
+            // its end rows are wrap columns whose outputs are discarded.  Tile j reads activation positions of conv1 tiles
+            // j-1..j+1 and its accumulator reuses the TMEM columns of conv1 tile j, drained by then.
+            constexpr uint32_t idesc2 = make_idesc(32);
             int ready = 0;
 #pragma unroll 1
             for (int j = 0; j < C::N2_TILES; ++j) {
-                const int need = j + 2 < C::N1_TILES - 1 ? j + 2 : C::N1_TILES - 1;
+                const int need = j + 1 < C::N1_TILES - 1 ? j + 1 : C::N1_TILES - 1;
                 for (; ready <= need; ++ready) mbar_wait(bar_mid + 8 * ready, 0);
                 tc_fence_after();
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int shift = (t / 3 - 1) * PW + (t % 3 - 1);
+                for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const uint32_t a0 = s_base + C::OFF_MID + (uint32_t)(2 * s * C::MID_PX + C::Q2_MIN + 128 * j + shift) * 16u;
-                        const uint32_t b0 = s_base + C::OFF_W2 + t * 1024 + s * 512;
-                        umma_f16(tmem + j * 16, make_desc(a0, C::MID_PX * 16, 128), make_desc(b0, 256, 128), idesc2, (t | s) > 0);
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t a0 = s_base + C::OFF_MID + (uint32_t)(2 * ks * C::MID_PX + C::Q2_MIN + 128 * j + (dy - 1) * PW) * 16u;
+                        const uint32_t b0 = s_base + C::OFF_W2 + (dy * 2 + ks) * 1024;
+                        umma_f16(tmem + j * 32, make_desc(a0, C::MID_PX * 16, 128), make_desc(b0, 512, 128), idesc2, (dy | ks) > 0);
                     }
                 }
                 umma_commit(bar_c2 + 8 * j);
@@ -361,22 +365,53 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
                 mbar_arrive(bar_mid + 8 * i);
             }
         }
-        // ---- epilogue 2: +b2, relu6, fp16 -> float ; softmax over the first 4 channels ; guidance = last 4
+        // ---- epilogue 2: combine the three dx blocks of neighbouring rows, +b2, relu6, fp16 -> float ; softmax / guidance
         {
             const float* bias = reinterpret_cast<const float*>(smem + C::OFF_BIAS) + 32;
-            for (int j = team; j < C::N2_TILES; j += 2) {
+            float4* xch = reinterpret_cast<float4*>(smem + C::OFF_XCH) + team * 16;   // [parity][pair][dir] x 2 float4
+            int it = 0;
+            for (int j = team; j < C::N2_TILES; j += 2, ++it) {
                 mbar_wait(bar_c2 + 8 * j, 0);
                 tc_fence_after();
-                uint32_t r[8];
-                tmem_ld8(tlane + j * 16, r);
+                uint32_t r[32];
+                tmem_ld32(tlane + j * 32, r);
+                // row r of the tile = position q; its output needs block 0 (dx=-1) of row r-1 and block 2 (dx=+1) of row r+1
+                float lft[8], rgt[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    lft[o] = __shfl_up_sync(0xffffffffu, __uint_as_float(r[o]), 1);
+                    rgt[o] = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + o]), 1);
+                }
+                // rows 31|32 and 95|96 of the tile (x = 31|32) sit in different warps: swap through shared memory
+                float4* xb = xch + (it & 1) * 8 + (sub >> 1) * 4;
+                if (!(sub & 1) && lane == 31) {
+                    xb[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                    xb[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                }
+                if ((sub & 1) && lane == 0) {
+                    xb[2] = make_float4(__uint_as_float(r[16]), __uint_as_float(r[17]), __uint_as_float(r[18]), __uint_as_float(r[19]));
+                    xb[3] = make_float4(__uint_as_float(r[20]), __uint_as_float(r[21]), __uint_as_float(r[22]), __uint_as_float(r[23]));
+                }
+                if (team == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");   // named barrier of this 4-warp team
+                else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                if ((sub & 1) && lane == 0) {
+                    const float4 u0 = xb[0], u1 = xb[1];
+                    lft[0] = u0.x; lft[1] = u0.y; lft[2] = u0.z; lft[3] = u0.w; lft[4] = u1.x; lft[5] = u1.y; lft[6] = u1.z; lft[7] = u1.w;
+                }
+                if (!(sub & 1) && lane == 31) {
+                    const float4 u0 = xb[2], u1 = xb[3];
+                    rgt[0] = u0.x; rgt[1] = u0.y; rgt[2] = u0.z; rgt[3] = u0.w; rgt[4] = u1.x; rgt[5] = u1.y; rgt[6] = u1.z; rgt[7] = u1.w;
+                }
                 const int q = C::Q2_MIN + 128 * j + row;
                 const int x = q & (PW - 1), y = q >> 6;
                 const int gx = bx + x - 2, gy = by + y - 2;
-                if (x >= 2 && x < TW + 2 && y >= 2 && y < TH + 2 && gx < W && gy < H && gy < d.y1) {
+                if (x >= 2 && x < TW + 2 && gx < W && gy < H && gy < d.y1) {
                     float o[8];
 #pragma unroll
                     for (int c = 0; c < 8; c += 2) {
-                        const uint32_t u = act_h2(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), bias[c], bias[c + 1], fused_bias);
+                        const float acc0 = (lft[c] + __uint_as_float(r[8 + c])) + rgt[c];
+                        const float acc1 = (lft[c + 1] + __uint_as_float(r[9 + c])) + rgt[c + 1];
+                        const uint32_t u = act_h2(acc0, acc1, bias[c], bias[c + 1], fused_bias);
                         __half2 h;
                         memcpy(&h, &u, 4);
                         const float2 f = __half22float2(h);

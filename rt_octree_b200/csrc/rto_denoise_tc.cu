@@ -15,9 +15,11 @@
 //     is the first one shifted by the descriptor's leading-dimension offset), accumulators in TMEM columns
 //     [32*i, 32*i+32);  epilogue 1 (tcgen05.ld -> +bias, relu6, fp16) writes the 32-channel activation back to
 //     shared memory as four 8-channel planes (again 16 B per pixel per plane), zero outside the image;
-//   * conv2: per M-tile 9 taps x 2 k-steps, N = 16 (8 real outputs), K = 16, A = two planes per k-step (LBO = plane
-//     stride); accumulators reuse TMEM columns already drained;  epilogue 2 -> +bias, relu6, fp16 -> fp32 softmax /
-//     guidance;
+//   * conv2: the three horizontal taps ride in N: D'[r][dx*8+o] = sum_{dy,c} mid[r+dy*64][c] w2[o][c][dy][dx] needs no
+//     x-shift of A, so an M-tile (two image rows) costs 3 dy x 2 k-steps = 6 MMAs (M128 N32 K16, LBO = plane stride) instead
+//     of 18; accumulators reuse TMEM columns already drained;  epilogue 2 adds D'[r-1][dx=-1] + D'[r][0] + D'[r+1][dx=+1]
+//     (warp shuffles; the two rows that straddle a warp boundary go through 64 bytes of shared memory) -> +bias, relu6,
+//     fp16 -> fp32 softmax / guidance;
 //   * the M-tiles are software-pipelined through single-use mbarriers: one MMA-issuing warp, two 4-warp epilogue teams
 //     (see the kernel);  256 TMEM columns and <= 110 KB of shared memory per CTA => two CTAs per SM.
 //

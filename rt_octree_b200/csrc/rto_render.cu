@@ -35,7 +35,7 @@ constexpr int kDefaultBlocksPerSM = 32 / kBlockWarps;      // tuned on B200 (too
 // Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
 //   [0, D]            ancestor stack (D = tree max depth)
 //   [D+1, D+1+SPP]    sorted thresholds + FLT_MAX sentinel
-//   [.., +SPP)        collided leaf ids      [.., +SPP) collision counts
+//   [.., +SPP)        collided leaf ids      [.., +SPP) collision counts      [.., +2) scratch floats
 template <int SPP>
 struct SmemRay {
     uint32_t* base;   // &smem[threadIdx.x]
@@ -44,7 +44,10 @@ struct SmemRay {
     __device__ __forceinline__ float& dst(int i) { return reinterpret_cast<float*>(base)[(off_dst + i) * kBlockThreads]; }
     __device__ __forceinline__ uint32_t& hit_leaf(int i) { return base[(off_dst + SPP + 1 + i) * kBlockThreads]; }
     __device__ __forceinline__ float& hit_cnt(int i) { return reinterpret_cast<float*>(base)[(off_dst + 2 * SPP + 1 + i) * kBlockThreads]; }
-    static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1; }   // max_depth = -1: no stack
+    // two floats the grid walker touches only when sigma > sigma_thresh (optical depth so far, delta_scale): parked here so
+    // the marching loop's registers go to loop invariants instead
+    __device__ __forceinline__ float& scratch(int i) { return reinterpret_cast<float*>(base)[(off_dst + 3 * SPP + 1 + i) * kBlockThreads]; }
+    static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1 + 2; }   // max_depth = -1: no stack
 };
 
 // Persistent kernel.  Work unit = a 16x8 pixel SUPER-TILE (2x2 warp tiles) claimed by a block from a global counter

@@ -21,6 +21,8 @@ struct HostRay {   // per-ray scratch (shared memory on the GPU: SmemRay in rto_
     float& dst(int i) { return d[i]; }
     uint32_t& hit_leaf(int i) { return hl[i]; }
     float& hit_cnt(int i) { return hc[i]; }
+    float sc[2];
+    float& scratch(int i) { return sc[i]; }
 };
 
 template <int SPP>

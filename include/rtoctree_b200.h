@@ -104,10 +104,27 @@ int rto_synchronize(void* stream);
 
 /* ---- tree : N3Tree::load_npz result -> N3Tree::load_cuda (src/n3tree.cpp:228-362, src/cuda/n3tree.cu:9-41) ----
  * Host arrays exactly as they sit in tree.npz: child int32 [capacity][N][N][N] (relative node offsets, 0 = leaf),
- * data fp16 [capacity][N][N][N][data_dim] (last = sigma).  The call uploads them and re-lays them out ON THE GPU
- * as structure-of-arrays (node words with embedded sigma + padded fp16 payload plane).  N must be 2. */
+ * data fp16 [capacity][N][N][N][data_dim] (last = sigma).  The call uploads them and builds every HBM plane ON THE GPU:
+ * node words with embedded sigma, the padded fp16 payload plane, the structure check (offsets in range, no cycles,
+ * depth) and the sparse brick grid the marching loop reads.  N must be 2. */
 int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, int64_t capacity, int N,
                     int data_dim, int format, int basis_dim, const float offset[3], const float scale[3]);
+/* Quantised / svox-compressed tree.npz (producer renderer/scripts/compress_octree.py:68-119; the reference decodes it on the
+ * host into the dense `data` array, renderer/src/n3tree.cpp:279-340).  Here the compressed arrays are uploaded as they sit
+ * in the file and gathered ON THE GPU straight into the payload plane:
+ *   quant_colors fp16 [n_quant][65536][3], quant_map u16 [n_quant][capacity][N][N][N], sigma fp16 [capacity][N][N][N],
+ *   data_retained fp16 [n_retained][capacity][N][N][N][3] (NULL when n_retained == 0);
+ *   colour slot j + n_retained + k*(n_quant+n_retained) of a leaf = quant_colors[j][quant_map[j][leaf]][k]   (:301-316),
+ *   colour slot j + k*(n_quant+n_retained)               of a leaf = data_retained[j][leaf][k]                (:325-338). */
+int rto_tree_create_quantized(rto_tree** out, const int32_t* child, int64_t capacity, int N, int data_dim, int format,
+                              int basis_dim, const float offset[3], const float scale[3], const void* quant_colors_f16,
+                              const uint16_t* quant_map, int n_quant, const void* sigma_f16, const void* data_retained_f16,
+                              int n_retained);
+/* Copy one device plane of the loaded tree back to the host (inspection / parity tests; the reference keeps the host
+ * arrays in N3Tree::data_ / child_ instead).  `bytes` must equal the plane size: nodes = rto_tree_info.node_bytes,
+ * payload = payload_bytes, grid top = 4 << (3*grid_level), grid bricks = n_bricks * 2048. */
+typedef enum rto_tree_plane { RTO_PLANE_NODES = 0, RTO_PLANE_PAYLOAD = 1, RTO_PLANE_GRID_TOP = 2, RTO_PLANE_GRID_BRICKS = 3 } rto_tree_plane;
+int rto_tree_read_plane(const rto_tree* tree, int plane, void* host_dst, size_t bytes);
 /* main_headless.cpp:400-405 / n3tree.hpp:69-71: NDC warp for forward-facing (llff) scenes; width<=0 disables. */
 int rto_tree_set_ndc(rto_tree* tree, float ndc_width, float ndc_height, float ndc_focal);
 int rto_tree_get_info(const rto_tree* tree, rto_tree_info* info);

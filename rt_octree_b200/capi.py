@@ -51,7 +51,7 @@ class TracePOD(C.Structure):
 
 EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py checks the library exports them all)
     "rto_last_error", "rto_abi_version", "rto_set_device", "rto_device_count", "rto_synchronize", "rto_render_options_default",
-    "rto_tree_create", "rto_tree_set_ndc", "rto_tree_get_info", "rto_tree_destroy",
+    "rto_tree_create", "rto_tree_create_quantized", "rto_tree_read_plane", "rto_tree_set_ndc", "rto_tree_get_info", "rto_tree_destroy",
     "rto_context_create", "rto_context_destroy", "rto_context_aux", "rto_context_image", "rto_context_rng_seed",
     "rto_context_rng_advance", "rto_context_rng_set_frame", "rto_context_rng_get", "rto_context_read_aux", "rto_context_write_aux", "rto_context_read_image_rgba8",
     "rto_context_read_image", "rto_render", "rto_render_rect", "rto_render_trace",
@@ -80,6 +80,8 @@ def load(path: str = LIB_PATH):
     L.rto_render_options_default.argtypes = [C.POINTER(RenderOptionsPOD)]
     L.rto_render_options_default.restype = None
     L.rto_tree_create.argtypes = [C.POINTER(P), P, P, C.c_int64, I, I, I, I, P, P]
+    L.rto_tree_create_quantized.argtypes = [C.POINTER(P), P, C.c_int64, I, I, I, I, P, P, P, P, I, P, P, I]
+    L.rto_tree_read_plane.argtypes = [P, I, P, C.c_size_t]
     L.rto_tree_set_ndc.argtypes = [P, F, F, F]
     L.rto_tree_get_info.argtypes = [P, C.POINTER(TreeInfoPOD)]
     L.rto_tree_destroy.argtypes = [P]
@@ -241,18 +243,45 @@ class N3Tree:
         self.offset = np.asarray(z["offset"], np.float32).reshape(3).copy()
         child = np.ascontiguousarray(z["child"], np.int32)
         self.N = int(child.shape[1])
+        self.capacity = int(child.shape[0])
+        L = load()
+        off, sc = self.offset.ctypes.data, self.scale.ctypes.data
         if "quant_colors" in z:
-            data = decode_quantized(z, child.shape[0], self.N, self.data_dim)
+            # codebook files go to the GPU as they are; the gather runs there (rto_tree_create_quantized)
+            qc = np.asarray(z["quant_colors"])
+            if qc.dtype != np.float16:
+                raise ValueError("codebook must be stored in half precision")
+            qm = np.ascontiguousarray(z["quant_map"], np.uint16)
+            if qc.shape[0] != qm.shape[0]:
+                raise ValueError("codebook and map basis numbers does not match")
+            qc = np.ascontiguousarray(qc)
+            sigma = np.ascontiguousarray(z["sigma"], np.float16)
+            ret = np.ascontiguousarray(z["data_retained"], np.float16) if "data_retained" in z else None
+            _check(L.rto_tree_create_quantized(C.byref(self._h), child.ctypes.data, self.capacity, self.N, self.data_dim,
+                                               self.format, self.basis_dim, off, sc, qc.ctypes.data, qm.ctypes.data,
+                                               int(qm.shape[0]), sigma.ctypes.data,
+                                               ret.ctypes.data if ret is not None else None,
+                                               int(ret.shape[0]) if ret is not None else 0))
         else:
             data = z["data"]
             if data.dtype != np.float16:
                 raise ValueError("data must be stored in half precision")
             data = np.ascontiguousarray(data)
-        self.capacity = int(child.shape[0])
-        fmt = self.format
-        L = load()
-        _check(L.rto_tree_create(C.byref(self._h), child.ctypes.data, data.ctypes.data, self.capacity, self.N,
-                                 self.data_dim, fmt, self.basis_dim, self.offset.ctypes.data, self.scale.ctypes.data))
+            _check(L.rto_tree_create(C.byref(self._h), child.ctypes.data, data.ctypes.data, self.capacity, self.N,
+                                     self.data_dim, self.format, self.basis_dim, off, sc))
+
+    PLANES = {"nodes": (0, np.uint32), "payload": (1, np.float16), "grid_top": (2, np.uint32), "grid_bricks": (3, np.uint32)}
+
+    def read_plane(self, name):
+        """Device plane copied back to the host (rto_tree_read_plane): nodes / payload / grid_top / grid_bricks."""
+        which, dt = self.PLANES[name]
+        i = self.info
+        nbytes = {"nodes": i.node_bytes, "payload": i.payload_bytes,
+                  "grid_top": (4 << (3 * i.grid_level)) if i.grid_level else 0,
+                  "grid_bricks": i.n_bricks * 2048 if i.grid_level else 0}[name]
+        out = np.empty(nbytes // np.dtype(dt).itemsize, dt)
+        _check(load().rto_tree_read_plane(self._h, which, out.ctypes.data, nbytes))
+        return out
 
     def set_ndc(self, width, height, focal):
         _check(load().rto_tree_set_ndc(self._h, float(width), float(height), float(focal)))

@@ -12,14 +12,10 @@
 #include <vector>
 
 #include "../../include/rtoctree_b200.h"
-#include "rto_grid_host.h"
 #include "rto_internal.h"
+#include "rto_tree.h"
 
 namespace rto {
-cudaError_t launch_build_nodes(const int32_t*, const __half*, int, int64_t, int64_t, uint32_t*, unsigned long long*,
-                               int*, cudaStream_t);
-cudaError_t launch_build_payload(const __half*, int, int, int64_t, __half*, cudaStream_t);
-int tree_max_depth_host(const int32_t* child, int64_t capacity);
 cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream);
 cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
                                float4* out, cudaStream_t stream);
@@ -151,102 +147,100 @@ void rto_render_options_default(rto_render_options* o) {
 }
 
 // ---------------------------------------------------------------------------------------------------- tree
-int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, int64_t capacity, int N,
-                    int data_dim, int format, int basis_dim, const float offset[3], const float scale[3]) {
-    if (!out || !child || !data_f16 || !offset || !scale) return fail(RTO_ERR_INVALID, "NULL argument");
-    *out = nullptr;
+// argument checks shared by the dense and the quantised entry point; normalises basis_dim for RGBA
+static int check_tree_args(int64_t capacity, int N, int data_dim, int format, int* basis_dim) {
     if (N != 2) return fail(RTO_ERR_UNSUPPORTED, "N == %d: only N = 2 octrees are supported (n3tree.cpp:273-275 warns the same)", N);
     if (capacity <= 0 || capacity >= (int64_t)1 << 28) return fail(RTO_ERR_INVALID, "capacity %lld out of range", (long long)capacity);
     if (format == RTO_FORMAT_SG || format == RTO_FORMAT_ASG)
         return fail(RTO_ERR_UNSUPPORTED, "SG/ASG data formats are not supported (SH and RGBA only)");
     if (format == RTO_FORMAT_SH) {
-        if (!(basis_dim == 1 || basis_dim == 4 || basis_dim == 9 || basis_dim == 16 || basis_dim == 25))
-            return fail(RTO_ERR_INVALID, "SH basis_dim %d not in {1,4,9,16,25}", basis_dim);
-        if (data_dim != 3 * basis_dim + 1) return fail(RTO_ERR_INVALID, "data_dim %d != 3*%d+1", data_dim, basis_dim);
+        const int b = *basis_dim;
+        if (!(b == 1 || b == 4 || b == 9 || b == 16 || b == 25))
+            return fail(RTO_ERR_INVALID, "SH basis_dim %d not in {1,4,9,16,25}", b);
+        if (data_dim != 3 * b + 1) return fail(RTO_ERR_INVALID, "data_dim %d != 3*%d+1", data_dim, b);
     } else if (format == RTO_FORMAT_RGBA) {
         if (data_dim != 4) return fail(RTO_ERR_INVALID, "RGBA format needs data_dim 4, got %d", data_dim);
-        basis_dim = -1;
+        *basis_dim = -1;
     } else {
         return fail(RTO_ERR_INVALID, "unknown data format %d", format);
     }
-    const int max_depth = rto::tree_max_depth_host(child, capacity);
-    if (max_depth < 0) return fail(RTO_ERR_INVALID, "malformed tree: child offset leaves the node array or the links form a cycle");
-    if (max_depth > RTO_COORD_BITS) return fail(RTO_ERR_UNSUPPORTED, "tree depth %d exceeds %d levels", max_depth, RTO_COORD_BITS);
+    return RTO_OK;
+}
 
+static int tree_from_source(rto_tree** out, const rto::TreeSource& src, int N, int format, int basis_dim,
+                            const float offset[3], const float scale[3]) {
     rto_tree* t = new (std::nothrow) rto_tree;
     if (!t) return fail(RTO_ERR_NOMEM, "out of host memory");
-    const int64_t n_entries = capacity * 8;
-    const int stride = ((data_dim - 1) + 7) / 8 * 8;
-    int32_t* d_child = nullptr;
-    __half* d_data = nullptr;
-    unsigned long long* d_cnt = nullptr;
-    int* d_bad = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_child); cudaFree(d_data); cudaFree(d_cnt); cudaFree(d_bad);
-    };
-    auto bail = [&](cudaError_t e, const char* what) {
-        cleanup();
-        cudaFree(t->nodes); cudaFree(t->payload);
+    rto::TreeBuilt b;
+    std::string err;
+    int64_t launches = 0;
+    const int rc = rto::build_tree_device(src, b, err, &launches);
+    g_launches += launches;
+    if (rc != RTO_OK) {
         delete t;
-        return fail(e == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-    };
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_child, n_entries * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc(child)");
-    if ((e = cudaMalloc(&d_data, (size_t)n_entries * data_dim * sizeof(__half))) != cudaSuccess) return bail(e, "cudaMalloc(data)");
-    if ((e = cudaMalloc(&t->nodes, n_entries * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc(nodes)");
-    if ((e = cudaMalloc(&t->payload, (size_t)n_entries * stride * sizeof(__half))) != cudaSuccess) return bail(e, "cudaMalloc(payload)");
-    if ((e = cudaMalloc(&d_cnt, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemset(d_cnt, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
-    if ((e = cudaMemset(d_bad, 0, sizeof(int))) != cudaSuccess) return bail(e, "cudaMemset");
-    if ((e = cudaMemcpy(d_child, child, n_entries * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D child");
-    if ((e = cudaMemcpy(d_data, data_f16, (size_t)n_entries * data_dim * sizeof(__half), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D data");
-    if ((e = rto::launch_build_nodes(d_child, d_data, data_dim, n_entries, capacity, t->nodes, d_cnt, d_bad, nullptr)) != cudaSuccess) return bail(e, "build_nodes");
-    if ((e = rto::launch_build_payload(d_data, data_dim, stride, n_entries, t->payload, nullptr)) != cudaSuccess) return bail(e, "build_payload");
-    g_launches += 2;
-    unsigned long long n_leaves = 0;
-    int bad = 0;
-    if ((e = cudaMemcpy(&n_leaves, d_cnt, sizeof n_leaves, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail(e, "D2H");
-    if ((e = cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail(e, "D2H");
-    cleanup();
-    if (bad) {
-        cudaFree(t->nodes); cudaFree(t->payload);
-        delete t;
-        return fail(RTO_ERR_INVALID, "malformed tree: child offset out of range");
+        return fail(rc, "%s", err.c_str());
     }
-    {   // sparse brick grid for the marching loop (skipped for very shallow / very deep trees or RTO_DISABLE_GRID=1)
-        const char* off = getenv("RTO_DISABLE_GRID");
-        std::vector<uint32_t> top, bricks;
-        int K = 0;
-        if (!(off && off[0] == '1') &&
-            rto::build_grid_host(child, static_cast<const uint16_t*>(data_f16), data_dim, capacity, max_depth, top, bricks, K) &&
-            bricks.size() / 512 < ((size_t)1 << 23)) {   // the marcher indexes brick words with 32 bits (rto_ray.cuh grid_lookup)
-            cudaError_t ge = cudaMalloc(&t->grid_top, top.size() * sizeof(uint32_t));
-            if (ge == cudaSuccess) ge = cudaMalloc(&t->grid_bricks, (bricks.empty() ? 512 : bricks.size()) * sizeof(uint32_t));
-            if (ge == cudaSuccess) ge = cudaMemcpy(t->grid_top, top.data(), top.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-            if (ge == cudaSuccess && !bricks.empty())
-                ge = cudaMemcpy(t->grid_bricks, bricks.data(), bricks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-            if (ge != cudaSuccess) {
-                cudaFree(t->nodes); cudaFree(t->payload); cudaFree(t->grid_top); cudaFree(t->grid_bricks);
-                delete t;
-                return fail(ge == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "grid upload: %s", cudaGetErrorString(ge));
-            }
-            t->grid_K = K;
-            t->n_bricks = (int64_t)(bricks.size() / 512);
-        }
-    }
+    t->nodes = b.nodes; t->payload = b.payload;
+    t->grid_top = b.grid_top; t->grid_bricks = b.grid_bricks;
+    t->grid_K = b.grid_K; t->n_bricks = b.n_bricks;
+    const int64_t n_entries = src.capacity * 8;
     rto_tree_info& I = t->info;
-    I.capacity = capacity; I.N = N; I.data_dim = data_dim; I.format = format; I.basis_dim = basis_dim;
-    I.max_depth = max_depth; I.n_leaves = (int64_t)n_leaves;
+    I.capacity = src.capacity; I.N = N; I.data_dim = src.data_dim; I.format = format; I.basis_dim = basis_dim;
+    I.max_depth = b.max_depth; I.n_leaves = b.n_leaves;
     I.node_bytes = n_entries * (int64_t)sizeof(uint32_t);
-    I.payload_bytes = n_entries * (int64_t)stride * (int64_t)sizeof(__half);
-    I.payload_stride_halfs = stride;
+    I.payload_bytes = n_entries * (int64_t)b.stride * (int64_t)sizeof(__half);
+    I.payload_stride_halfs = b.stride;
     I.grid_level = t->grid_K;
     I.n_bricks = t->n_bricks;
     I.grid_bytes = t->grid_K ? (int64_t)((((size_t)1 << (3 * t->grid_K)) + (size_t)t->n_bricks * 512) * sizeof(uint32_t)) : 0;
     for (int i = 0; i < 3; ++i) { I.offset[i] = offset[i]; I.scale[i] = scale[i]; }
     I.ndc_width = -1.f; I.ndc_height = 0.f; I.ndc_focal = 0.f;
     *out = t;
+    return RTO_OK;
+}
+
+int rto_tree_create(rto_tree** out, const int32_t* child, const void* data_f16, int64_t capacity, int N,
+                    int data_dim, int format, int basis_dim, const float offset[3], const float scale[3]) {
+    if (!out || !child || !data_f16 || !offset || !scale) return fail(RTO_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (int rc = check_tree_args(capacity, N, data_dim, format, &basis_dim)) return rc;
+    rto::TreeSource src;
+    src.child = child; src.capacity = capacity; src.data_dim = data_dim; src.data_f16 = data_f16;
+    return tree_from_source(out, src, N, format, basis_dim, offset, scale);
+}
+
+int rto_tree_create_quantized(rto_tree** out, const int32_t* child, int64_t capacity, int N, int data_dim, int format,
+                              int basis_dim, const float offset[3], const float scale[3], const void* quant_colors_f16,
+                              const uint16_t* quant_map, int n_quant, const void* sigma_f16, const void* data_retained_f16,
+                              int n_retained) {
+    if (!out || !child || !offset || !scale || !sigma_f16) return fail(RTO_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (int rc = check_tree_args(capacity, N, data_dim, format, &basis_dim)) return rc;
+    if (n_quant < 0 || n_retained < 0 || (n_quant > 0 && (!quant_colors_f16 || !quant_map)) || (n_retained > 0 && !data_retained_f16))
+        return fail(RTO_ERR_INVALID, "NULL codebook / map / retained array");
+    // n3tree.cpp:301-316 writes data[j + n_ret + k*n_basis], k < 3: the colour part must hold 3 * n_basis values
+    if (n_quant + n_retained == 0 || 3 * (n_quant + n_retained) > data_dim - 1)
+        return fail(RTO_ERR_INVALID, "quantised tree: 3*(%d codebooks + %d retained) does not fit data_dim-1 = %d", n_quant, n_retained, data_dim - 1);
+    rto::TreeSource src;
+    src.child = child; src.capacity = capacity; src.data_dim = data_dim;
+    src.quant_colors = quant_colors_f16; src.quant_map = quant_map; src.sigma_f16 = sigma_f16;
+    src.retained_f16 = data_retained_f16; src.n_q = n_quant; src.n_ret = n_retained;
+    return tree_from_source(out, src, N, format, basis_dim, offset, scale);
+}
+
+int rto_tree_read_plane(const rto_tree* t, int plane, void* host_dst, size_t bytes) {
+    if (!t || !host_dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    const void* src = nullptr;
+    size_t have = 0;
+    switch (plane) {
+        case RTO_PLANE_NODES: src = t->nodes; have = (size_t)t->info.node_bytes; break;
+        case RTO_PLANE_PAYLOAD: src = t->payload; have = (size_t)t->info.payload_bytes; break;
+        case RTO_PLANE_GRID_TOP: src = t->grid_top; have = t->grid_K ? ((size_t)1 << (3 * t->grid_K)) * sizeof(uint32_t) : 0; break;
+        case RTO_PLANE_GRID_BRICKS: src = t->grid_bricks; have = t->grid_K ? (size_t)t->n_bricks * 512 * sizeof(uint32_t) : 0; break;
+        default: return fail(RTO_ERR_INVALID, "unknown plane %d", plane);
+    }
+    if (bytes != have) return fail(RTO_ERR_INVALID, "plane %d holds %zu bytes, caller asked for %zu", plane, have, bytes);
+    if (bytes) RTO_CUDA(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
     return RTO_OK;
 }
 

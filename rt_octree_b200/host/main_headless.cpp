@@ -460,7 +460,7 @@ int main(int argc, char* argv[]) {
     if (args.has("dry_run")) {
         rtohost::npz_t z = rtohost::npz_load(tree_path);
         N3Tree::HostArrays h;
-        N3Tree::decode_npz(z, h);
+        N3Tree::decode_npz(z, h, /*decode_on_host=*/true);
         printf("{\"poses\": %zu, \"width\": %d, \"height\": %d, \"fx\": %.9g, \"fy\": %.9g, \"spp\": %d, \"denoise\": %s, "
                "\"step_size\": %.9g, \"sigma_thresh\": %.9g, \"background\": %.9g, \"capacity\": %d, \"data_dim\": %d, "
                "\"data_format\": \"%s\", \"child_fnv\": \"%016llx\", \"data_fnv\": \"%016llx\", \"pose0\": [",

@@ -115,11 +115,17 @@ struct N3Tree {
         const int32_t* child = nullptr;
         const unsigned char* data = nullptr;      // fp16 [cap][N][N][N][data_dim]
         size_t n_child = 0;
-        std::vector<unsigned char> decoded;       // owns `data` for quantised files
+        std::vector<unsigned char> decoded;       // owns `data` for quantised files decoded on the host (--dry_run)
+        // quantised files (src/n3tree.cpp:279-340): the compressed arrays as they sit in the npz
+        bool quantized = false;
+        const uint16_t *quant_colors = nullptr, *quant_map = nullptr, *sigma = nullptr, *retained = nullptr;
+        int n_quant = 0, n_retained = 0;
     };
 
-    // N3Tree::load_npz (src/n3tree.cpp:228-362) without the upload
-    static void decode_npz(rtohost::npz_t& npz, HostArrays& h) {
+    // N3Tree::load_npz (src/n3tree.cpp:228-362) without the upload.  Quantised files: the load path hands the compressed
+    // arrays to rto_tree_create_quantized (codebook gather on the GPU); `decode_on_host` materialises the dense `data`
+    // array on the host instead, for `volrend_headless --dry_run`, which has to work without a device.
+    static void decode_npz(rtohost::npz_t& npz, HostArrays& h, bool decode_on_host) {
         auto need = [&](const char* k) -> rtohost::NpyArray& {
             auto it = npz.find(k);
             if (it == npz.end()) throw std::runtime_error(std::string("tree.npz: missing key '") + k + "'");
@@ -165,12 +171,17 @@ struct N3Tree {
             int n_basis = (int)qm.shape[0];
             if ((int)qc.shape[0] != n_basis) throw std::runtime_error("codebook and map basis numbers does not match");
             const int n_ret = npz.count("data_retained") ? (int)npz["data_retained"].shape[0] : 0;
-            n_basis += n_ret;
-            h.decoded.assign(n_child * (size_t)data_dim * 2, 0);
-            uint16_t* out = reinterpret_cast<uint16_t*>(h.decoded.data());
             const uint16_t* sig = need("sigma").data<uint16_t>();
             const uint16_t* map = qm.data<uint16_t>();
             const uint16_t* col = qc.data<uint16_t>();
+            const uint16_t* r = n_ret ? npz["data_retained"].data<uint16_t>() : nullptr;
+            h.quantized = true;
+            h.quant_colors = col; h.quant_map = map; h.sigma = sig; h.retained = r;
+            h.n_quant = n_basis; h.n_retained = n_ret;
+            if (!decode_on_host) return;
+            n_basis += n_ret;
+            h.decoded.assign(n_child * (size_t)data_dim * 2, 0);
+            uint16_t* out = reinterpret_cast<uint16_t*>(h.decoded.data());
             for (size_t i = 0; i < n_child; ++i) {
                 const size_t off = i * (size_t)data_dim;
                 for (int j = 0; j < n_basis - n_ret; ++j) {
@@ -181,15 +192,12 @@ struct N3Tree {
                 }
                 out[off + data_dim - 1] = sig[i];
             }
-            if (n_ret) {
-                const uint16_t* r = npz["data_retained"].data<uint16_t>();
-                for (size_t i = 0; i < n_child; ++i)
-                    for (int j = 0; j < n_ret; ++j) {
-                        size_t boff = i * (size_t)data_dim + j;
-                        const uint16_t* c = r + (size_t)j * n_child * 3 + i * 3;
-                        for (int k = 0; k < 3; ++k) { out[boff] = c[k]; boff += n_basis; }
-                    }
-            }
+            for (size_t i = 0; n_ret && i < n_child; ++i)
+                for (int j = 0; j < n_ret; ++j) {
+                    size_t boff = i * (size_t)data_dim + j;
+                    const uint16_t* c = r + (size_t)j * n_child * 3 + i * 3;
+                    for (int k = 0; k < 3; ++k) { out[boff] = c[k]; boff += n_basis; }
+                }
             h.data = h.decoded.data();
         } else {
             const rtohost::NpyArray& d = need("data");
@@ -202,12 +210,18 @@ struct N3Tree {
    private:
     void load_npz(rtohost::npz_t& npz) {
         HostArrays h;
-        decode_npz(npz, h);
+        decode_npz(npz, h, /*decode_on_host=*/false);
         N = h.N; data_dim = h.data_dim; capacity = h.capacity; data_format = h.data_format; scale = h.scale; offset = h.offset;
         printf("INFO: Scale %f %f %f\n", scale[0], scale[1], scale[2]);
-        rto_check(rto_tree_create(&device, h.child, h.data, capacity, N, data_dim, (int)data_format.format,
-                                  data_format.basis_dim, offset.data(), scale.data()),
-                  "rto_tree_create");
+        if (h.quantized)
+            rto_check(rto_tree_create_quantized(&device, h.child, capacity, N, data_dim, (int)data_format.format,
+                                                data_format.basis_dim, offset.data(), scale.data(), h.quant_colors,
+                                                h.quant_map, h.n_quant, h.sigma, h.retained, h.n_retained),
+                      "rto_tree_create_quantized");
+        else
+            rto_check(rto_tree_create(&device, h.child, h.data, capacity, N, data_dim, (int)data_format.format,
+                                      data_format.basis_dim, offset.data(), scale.data()),
+                      "rto_tree_create");
     }
 };
 

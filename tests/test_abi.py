@@ -49,12 +49,13 @@ def test_argument_validation_without_gpu(capi):
     assert lib.rto_tree_create(*args(fmt=capi.FORMAT_SG)) == capi.RTO_ERR_UNSUPPORTED
     assert lib.rto_tree_create(*args(bd=7)) == capi.RTO_ERR_INVALID
     assert lib.rto_tree_create(*args(dd=27)) == capi.RTO_ERR_INVALID
-    bad_child = np.zeros(8, np.int32)
-    bad_child[3] = 5  # points outside a 1-node tree
-    a = args()
-    a[1] = bad_child.ctypes.data
-    assert lib.rto_tree_create(*a) == capi.RTO_ERR_INVALID
-    assert b"malformed tree" in lib.rto_last_error()
+    # (the structure check of the child array — offsets in range, no cycles, depth — runs on the device:
+    #  tests/test_gpu_tree.py::test_malformed_trees_are_rejected)
+    q = lambda **kw: [C.byref(h), child.ctypes.data, 1, 2, 28, capi.FORMAT_SH, 9, off.ctypes.data, off.ctypes.data,
+                      data.ctypes.data, data.ctypes.data, kw.get("nq", 9), data.ctypes.data, None, kw.get("nr", 0)]
+    assert lib.rto_tree_create_quantized(*q(nq=10)) == capi.RTO_ERR_INVALID   # 3*10 colour slots do not fit data_dim-1 = 27
+    assert lib.rto_tree_create_quantized(*q(nq=8, nr=1)) == capi.RTO_ERR_INVALID   # retained basis without its array
+    assert lib.rto_tree_read_plane(None, 0, data.ctypes.data, 0) == capi.RTO_ERR_INVALID
     assert lib.rto_context_create(C.byref(h), 0, 10) == capi.RTO_ERR_INVALID
     w = np.zeros(4096, np.float16)
     assert lib.rto_net_create(C.byref(h), w.ctypes.data, w.ctypes.data, w.ctypes.data, w.ctypes.data, 8, 32, 7) == capi.RTO_ERR_UNSUPPORTED

@@ -188,6 +188,43 @@ def test_cli_matches_reference_cli(cli, tmp_path, mid_tree, net_weights, denoise
 
 
 @pytest.mark.gpu
+def test_cli_quantized_tree_matches_reference_cli(cli, tmp_path, small_tree, net_weights):
+    """A svox-compressed file: the reference CLI decodes the codebooks on the host (n3tree.cpp:279-340), this CLI hands the
+    compressed arrays to rto_tree_create_quantized (gather on the GPU).  Same aux buffers."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/volrend_headless not built")
+    import make_ts_module as M
+    from rt_octree_b200 import synthetic as S
+
+    cap, basis, n_ret = small_tree["child"].shape[0], 9, 1
+    rs = np.random.default_rng(2)
+    z = {k: small_tree[k] for k in ("data_dim", "data_format", "invradius3", "offset", "child")}
+    z["quant_colors"] = (rs.normal(size=(basis - n_ret, 65536, 3)) * 0.5).astype(np.float16)
+    z["quant_map"] = rs.integers(0, 65536, size=(basis - n_ret, cap, 2, 2, 2)).astype(np.uint16)
+    z["sigma"] = np.ascontiguousarray(small_tree["data"][..., -1])
+    z["data_retained"] = rs.normal(size=(n_ret, cap, 2, 2, 2, 3)).astype(np.float16)
+    npz = str(tmp_path / "tree_q.npz")
+    np.savez_compressed(npz, **z)
+    pj = str(tmp_path / "transforms_test.json")
+    S.write_blender_json(pj, S.make_poses(8)[:2])
+    oj = str(tmp_path / "opt.json")
+    S.write_opt_json(oj, spp=4, denoise=False)
+    ts = M.make_ts(net_weights, str(tmp_path / "ts_latest.ts"), device="cuda")   # both CLIs construct the denoiser up front
+    np.savez(str(tmp_path / "ts_latest.ts.npz"), **net_weights)
+    common = [npz, pj, "--options", oj, "--ts_module", ts, "-w", "160", "-h", "120", "--write_buffer"]
+    out_ref, out_us = str(tmp_path / "ref"), str(tmp_path / "us")
+    r = subprocess.run([REF_CLI, *common, "-o", out_ref], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    u = subprocess.run([cli, *common, "-o", out_us], capture_output=True, text=True, timeout=600)
+    assert u.returncode == 0, u.stderr[-1500:]
+    for i in range(2):
+        a = np.fromfile(os.path.join(out_ref, "buf_r_%d.bin" % i), np.float32).reshape(8, 120, 160)
+        b = np.fromfile(os.path.join(out_us, "buf_r_%d.bin" % i), np.float32).reshape(8, 120, 160)
+        assert a[3].max() == 1.0 and np.array_equal(a[3], b[3])
+        assert np.abs(a - b).max() < 1e-5
+
+
+@pytest.mark.gpu
 def test_cli_num_gpus_frame_sharding(cli, tmp_path, mid_tree, net_weights, capi):
     """--num_gpus N (one host thread per GPU, contiguous pose shards): every frame equals the single-GPU run bit for bit.
     Needs >= 2 visible GPUs (per-device function attributes, per-device L2 set-aside); skipped on a 1-GPU box."""

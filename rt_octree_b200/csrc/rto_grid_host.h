@@ -59,4 +59,10 @@ inline bool build_grid_host(const int32_t* child, const uint16_t* data, int data
     return true;
 }
 
+// byte plane of the bricks (rto_ray.cuh brick_byte): depth | 0x80 where sigma is non-zero
+inline void grid_bytes_host(const std::vector<uint32_t>& bricks, std::vector<uint8_t>& bricks8) {
+    bricks8.resize(bricks.size());
+    for (size_t i = 0; i < bricks.size(); ++i) bricks8[i] = brick_byte(bricks[i]);
+}
+
 }  // namespace rto

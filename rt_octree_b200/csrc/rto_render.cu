@@ -80,7 +80,9 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
 
 // GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent; TRACE builds
 // always use the tree walker because they must report the leaf visited at every step.
-template <int SPP, bool TRACE, bool GRID>
+// GRID: 0 = tree walker, 1 = brick grid read through the 4-byte leaf words, 2 = brick grid read through the byte plane
+// (production; RTO_GRID8=0 selects 1 for A/B runs).
+template <int SPP, bool TRACE, int GRID>
 __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RENDER_MIN_BLOCKS : 4)) * 4 / kBlockWarps) render_kernel(const __grid_constant__ RenderArgs a) {
     static_assert(!(TRACE && GRID), "trace builds use the tree walker");
     extern __shared__ uint32_t ray_smem[];
@@ -126,8 +128,8 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             auto sink = [&](uint32_t step, uint32_t leaf) {
                 if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
             };
-            if constexpr (GRID)
-                walk_grid<SPP, false>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+            if constexpr (GRID != 0)
+                walk_grid<SPP, false, GRID == 2>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             else
                 walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             const uint32_t sh_nums = wo.n_hits;
@@ -265,14 +267,16 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
     const bool grid_path = !trace && a.tree.grid.K > 0;
-    const int v = trace ? 1 : (grid_path ? 2 : 0);
+    const char* g8 = getenv("RTO_GRID8");   // read per launch so that one process can A/B the two planes
+    const bool grid8 = grid_path && !(g8 && g8[0] == '0') && a.tree.grid.bricks8 != nullptr;
+    const int v = trace ? 1 : (grid_path ? (grid8 ? 3 : 2) : 0);
     const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
     // Function attributes, occupancy and the L2 set-aside are per DEVICE (the CLI drives one host thread per GPU), so the
     // cached launch state is indexed by the current device; slots of different devices are never shared between threads.
     struct DevState {
         int num_sms = 0;
-        size_t smem_set[3] = {0, 0, 0};
-        int occ_limit[3] = {0, 0, 0};
+        size_t smem_set[4] = {0, 0, 0, 0};
+        int occ_limit[4] = {0, 0, 0, 0};
         int persist = -1, max_win = 0, max_persist = 0;
     };
     static DevState dev_state[kMaxDevices];
@@ -280,7 +284,8 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevState& ds = dev_state[dev >= 0 && dev < kMaxDevices ? dev : 0];
-    void (*kern)(RenderArgs) = trace ? render_kernel<SPP, true, false> : (grid_path ? render_kernel<SPP, false, true> : render_kernel<SPP, false, false>);
+    void (*kern)(RenderArgs) = trace ? render_kernel<SPP, true, 0>
+                               : (grid8 ? render_kernel<SPP, false, 2> : (grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>));
     if (smem > ds.smem_set[v] || ds.occ_limit[v] == 0) {   // first launch on this device, or a deeper tree than any seen before
         if ((e = cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -305,7 +310,8 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         }
     }
     if (ds.persist && grid_path && a.tree.grid_brick_bytes > 0) {
-        size_t bytes = a.tree.grid_brick_bytes;
+        // the plane the marching loop reads on (almost) every step: the byte bricks when they are in use
+        size_t bytes = grid8 ? a.tree.grid_brick_bytes / sizeof(uint32_t) : a.tree.grid_brick_bytes;
         if (ds.max_win > 0 && bytes > (size_t)ds.max_win) bytes = (size_t)ds.max_win;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
@@ -314,7 +320,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        at[0].val.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(a.tree.grid.bricks);
+        at[0].val.accessPolicyWindow.base_ptr = grid8 ? (void*)const_cast<uint8_t*>(a.tree.grid.bricks8) : (void*)const_cast<uint32_t*>(a.tree.grid.bricks);
         at[0].val.accessPolicyWindow.num_bytes = bytes;
         at[0].val.accessPolicyWindow.hitRatio = bytes <= (size_t)ds.max_persist ? 1.0f : (float)ds.max_persist / (float)bytes;
         at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;

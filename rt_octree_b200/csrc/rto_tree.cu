@@ -18,7 +18,7 @@
 //   grid_top_kernel               nodes                   -> top table leaf words / level-K node ids
 //   grid_scan_kernel              per-block brick counts  -> exclusive offsets
 //   grid_assign_kernel            ids in the host builder's order -> top table brick ids, brick -> node map
-//   grid_brick_kernel             nodes                   -> bricks
+//   grid_brick_kernel             nodes                   -> bricks (leaf words) + byte bricks (depth | dense flag)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -226,7 +226,7 @@ __global__ void grid_assign_kernel(const uint32_t* __restrict__ cell_node, const
 
 // one 512-thread block per brick, one thread per finest-level cell: at most 3 more look-ups below the level-K node
 __global__ void grid_brick_kernel(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ brick_node, int K,
-                                  uint32_t* __restrict__ bricks) {
+                                  uint32_t* __restrict__ bricks, uint8_t* __restrict__ bricks8) {
     const uint32_t b = blockIdx.x;
     const uint32_t c = threadIdx.x;   // == brick_cell_index(lx, ly, lz)
     const uint32_t lx = c >> 6, ly = (c >> 3) & 7u, lz = c & 7u;
@@ -243,6 +243,7 @@ __global__ void grid_brick_kernel(const uint32_t* __restrict__ nodes, const uint
         node = word;
     }
     bricks[(size_t)b * 512 + c] = out;
+    bricks8[(size_t)b * 512 + c] = brick_byte(out);
 }
 
 // --------------------------------------------------------------------------------------------------- host driver
@@ -304,7 +305,7 @@ static int grid_build_device(const uint32_t* nodes, int max_depth, TreeBuilt& ou
     const uint32_t n_cells = 1u << (3 * K);
     const int B = 256;
     const unsigned nb = blocks_for(n_cells, B);
-    DevBuf top, cell_node, block_count, total, brick_node, bricks;
+    DevBuf top, cell_node, block_count, total, brick_node, bricks, bricks8;
     RTO_TRY(top.alloc((size_t)n_cells * sizeof(uint32_t)), "cudaMalloc(grid top)");
     RTO_TRY(cell_node.alloc((size_t)n_cells * sizeof(uint32_t)), "cudaMalloc(grid scratch)");
     RTO_TRY(block_count.alloc((size_t)nb * sizeof(uint32_t)), "cudaMalloc(grid scratch)");
@@ -319,17 +320,19 @@ static int grid_build_device(const uint32_t* nodes, int max_depth, TreeBuilt& ou
     if ((size_t)n_bricks >= ((size_t)1 << 23)) return RTO_OK;   // the marcher indexes brick words with 32 bits (grid_lookup)
     RTO_TRY(brick_node.alloc((size_t)n_bricks * sizeof(uint32_t)), "cudaMalloc(grid scratch)");
     RTO_TRY(bricks.alloc((size_t)(n_bricks ? n_bricks : 1) * 512 * sizeof(uint32_t)), "cudaMalloc(grid bricks)");
+    RTO_TRY(bricks8.alloc((size_t)(n_bricks ? n_bricks : 1) * 512), "cudaMalloc(grid byte bricks)");
     if (n_bricks) {
         grid_assign_kernel<<<nb, B>>>(cell_node.as<uint32_t>(), block_count.as<uint32_t>(), K, n_cells, top.as<uint32_t>(),
                                       brick_node.as<uint32_t>());
         RTO_TRY(cudaGetLastError(), "grid_assign_kernel");
-        grid_brick_kernel<<<n_bricks, 512>>>(nodes, brick_node.as<uint32_t>(), K, bricks.as<uint32_t>());
+        grid_brick_kernel<<<n_bricks, 512>>>(nodes, brick_node.as<uint32_t>(), K, bricks.as<uint32_t>(), bricks8.as<uint8_t>());
         RTO_TRY(cudaGetLastError(), "grid_brick_kernel");
         *launches += 2;
     }
     RTO_TRY(cudaDeviceSynchronize(), "grid build");
     out.grid_top = top.release<uint32_t>();
     out.grid_bricks = bricks.release<uint32_t>();
+    out.grid_bricks8 = bricks8.release<uint8_t>();
     out.grid_K = K;
     out.n_bricks = n_bricks;
     return RTO_OK;
@@ -343,21 +346,27 @@ static int grid_build_host(const TreeSource& s, int max_depth, TreeBuilt& out, c
     if (!build_grid_host(s.child, static_cast<const uint16_t*>(s.data_f16), s.data_dim, s.capacity, max_depth, top, bricks, K) ||
         bricks.size() / 512 >= ((size_t)1 << 23))
         return RTO_OK;
-    DevBuf dt, db;
+    std::vector<uint8_t> bricks8;
+    grid_bytes_host(bricks, bricks8);
+    DevBuf dt, db, d8;
     RTO_TRY(dt.alloc(top.size() * sizeof(uint32_t)), "cudaMalloc(grid top)");
     RTO_TRY(db.alloc((bricks.empty() ? 512 : bricks.size()) * sizeof(uint32_t)), "cudaMalloc(grid bricks)");
+    RTO_TRY(d8.alloc(bricks.empty() ? 512 : bricks.size()), "cudaMalloc(grid byte bricks)");
     RTO_TRY(cudaMemcpy(dt.p, top.data(), top.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D grid top");
-    if (!bricks.empty())
+    if (!bricks.empty()) {
         RTO_TRY(cudaMemcpy(db.p, bricks.data(), bricks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D grid bricks");
+        RTO_TRY(cudaMemcpy(d8.p, bricks8.data(), bricks8.size(), cudaMemcpyHostToDevice), "H2D grid byte bricks");
+    }
     out.grid_top = dt.release<uint32_t>();
     out.grid_bricks = db.release<uint32_t>();
+    out.grid_bricks8 = d8.release<uint8_t>();
     out.grid_K = K;
     out.n_bricks = (int64_t)(bricks.size() / 512);
     return RTO_OK;
 }
 
 void tree_built_free(TreeBuilt& b) {
-    cudaFree(b.nodes); cudaFree(b.payload); cudaFree(b.grid_top); cudaFree(b.grid_bricks);
+    cudaFree(b.nodes); cudaFree(b.payload); cudaFree(b.grid_top); cudaFree(b.grid_bricks); cudaFree(b.grid_bricks8);
     b = TreeBuilt{};
 }
 
@@ -437,7 +446,7 @@ int build_tree_device(const TreeSource& s, TreeBuilt& out, std::string& err, int
         int rc;
         if (how && how[0] == 'h' && !quant) rc = grid_build_host(s, depth, out, fail);
         else rc = grid_build_device(nodes.as<uint32_t>(), depth, out, launches, fail);
-        if (rc) { cudaFree(out.grid_top); cudaFree(out.grid_bricks); out = TreeBuilt{}; return rc; }
+        if (rc) { tree_built_free(out); return rc; }
     }
     out.nodes = nodes.release<uint32_t>();
     out.payload = payload.release<__half>();

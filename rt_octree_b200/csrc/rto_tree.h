@@ -25,6 +25,7 @@ struct TreeBuilt {   // device planes, owned by the caller after a successful bu
     __half* payload = nullptr;
     uint32_t* grid_top = nullptr;
     uint32_t* grid_bricks = nullptr;
+    uint8_t* grid_bricks8 = nullptr;   // byte plane of the bricks (rto_ray.cuh GridDev)
     int grid_K = 0;
     int64_t n_bricks = 0;
     int64_t n_leaves = 0;

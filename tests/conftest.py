@@ -65,6 +65,8 @@ def host_ray_lib():
     lib.host_ray_walk.argtypes = [P, I, P, P, P, F, F, F, F, F, F, F, I, I, I, U64, U64, I, I, P] + [P] * 11 + [I]
     lib.host_ray_set_grid.restype = I
     lib.host_ray_set_grid.argtypes = [P, P, I, C.c_int64, I, P]
+    lib.host_ray_use_byte_bricks.restype = None
+    lib.host_ray_use_byte_bricks.argtypes = [I]
     return lib
 
 

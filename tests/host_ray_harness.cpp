@@ -46,8 +46,10 @@ void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameP
         auto sink = [&](uint32_t step, uint32_t leaf) {
             if (leaf_seq && (int)step < max_seq) leaf_seq[r * max_seq + step] = (int32_t)leaf;
         };
-        if (grid)
-            walk_grid<SPP, true>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+        if (grid && grid->bricks8)
+            walk_grid<SPP, true, true>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+        else if (grid)
+            walk_grid<SPP, true, false>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
         else
             walk<SPP, true>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
         steps[r] = wo.steps; term[r] = wo.term; src_bits[r] = u_bits(wo.src); t_bits[r] = u_bits(wo.t);
@@ -64,8 +66,16 @@ void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameP
 }  // namespace
 
 static std::vector<uint32_t> g_top, g_bricks;
-static GridDev g_grid{nullptr, nullptr, 0};
+static std::vector<uint8_t> g_bricks8;
+static GridDev g_grid{nullptr, nullptr, 0, nullptr};
 static bool g_grid_on = false;
+static bool g_byte_bricks = true;
+
+// 1 (default): walk_grid reads the byte plane like the production kernel; 0: the 4-byte leaf words (RTO_GRID8=0 variant)
+extern "C" void host_ray_use_byte_bricks(int on) {
+    g_byte_bricks = on != 0;
+    g_grid.bricks8 = g_byte_bricks && !g_bricks8.empty() ? g_bricks8.data() : nullptr;
+}
 
 // Build (or drop, child == NULL) the sparse brick grid used by subsequent host_ray_walk calls.
 // Returns K (0 = not built for this depth), n_bricks through *n_bricks.
@@ -76,7 +86,8 @@ extern "C" int host_ray_set_grid(const int32_t* child, const uint16_t* data, int
     int K = 0;
     if (!build_grid_host(child, data, data_dim, capacity, max_depth, g_top, g_bricks, K)) return 0;
     if (g_bricks.empty()) g_bricks.assign(512, 0u);
-    g_grid = make_grid_dev(g_top.data(), g_bricks.data(), K);
+    grid_bytes_host(g_bricks, g_bricks8);
+    g_grid = make_grid_dev(g_top.data(), g_bricks.data(), K, g_byte_bricks ? g_bricks8.data() : nullptr);
     g_grid_on = true;
     if (n_bricks) *n_bricks = (int64_t)(g_bricks.size() / 512);
     return K;

@@ -249,6 +249,35 @@ def test_grid_kernel_equals_tree_walker(capi, oracle, mid_tree, poses8, spp):
         assert aux_grid[3].max() == 1.0
 
 
+def test_byte_brick_plane_equals_word_plane(capi, mid_tree, poses8, monkeypatch):
+    """The marching loop reads the byte plane of the bricks (depth | dense flag) and fetches the 4-byte leaf word only in
+    cells with non-zero sigma; RTO_GRID8=0 reads the leaf words on every step.  Same words => identical buffers, also
+    with a NEGATIVE sigma threshold (then every sigma = 0 cell counts as dense) and with negative-zero sigmas."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H = 240, 176
+    fx = S.blender_focal(W)
+    tree = dict(mid_tree)
+    data = tree["data"].copy()
+    sig = data[..., -1].view(np.uint16)
+    leaf0 = (tree["child"] == 0) & (sig == 0)
+    flip = leaf0 & (np.random.RandomState(1).rand(*leaf0.shape) < 0.3)
+    sig[flip] = 0x8000                                       # -0.0: non-zero bits, still "not above" any threshold >= 0
+    tree["data"] = data
+    for tr_, thresh in ((mid_tree, 1e-2), (mid_tree, -1.0), (tree, 1e-2), (tree, 0.0)):
+        t, ctx, cam = _setup(capi, tr_, W, H, fx)
+        cam.transform = poses8[3]
+        out = {}
+        for g8 in ("1", "0"):
+            monkeypatch.setenv("RTO_GRID8", g8)
+            ctx.rng_set_frame(3)
+            capi.launch_renderer(t, cam, _opts(capi, 6, sigma_thresh=thresh), ctx)
+            out[g8] = (ctx.read_aux().copy(), ctx.read_image().copy())
+        monkeypatch.delenv("RTO_GRID8")
+        assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+        assert out["1"][0][3].max() == 1.0
+
+
 def test_tt_shaped_depth10_1080p(capi, oracle):
     """BASELINE config 4 shape: anisotropic depth-10 tree, 1920x1080, OpenCV-convention poses through the tt loader math.
     Size-independent properties on the full frame + bit-exact oracle on sampled rows."""

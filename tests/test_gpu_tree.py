@@ -57,6 +57,11 @@ def test_planes_and_device_grid_equal_host_builder(capi, depth):
     if br_d.size:
         d = ((br_d >> 23) & 0xff).astype(np.int64) - 127
         assert np.all(br_d & 0x80000000) and d.min() > depth - 3 and d.max() == depth
+        # byte plane (rto_ray.cuh brick_byte): depth | 0x80 where the sigma bits are non-zero
+        b8 = t.read_plane("grid_bricks8")
+        assert np.array_equal(b8, (d | np.where(br_d & 0xffff, 0x80, 0)).astype(np.uint8))
+        assert np.array_equal(b8, h.read_plane("grid_bricks8"))
+        assert (b8 & 0x80).any() and not (b8 & 0x80).all()
 
 
 def test_device_grid_bench_tree_equals_host_builder(capi):

@@ -52,6 +52,25 @@ def test_oracle_matches_live_reference_cpu(oracle, mid_tree, poses8, spp):
         assert np.array_equal(o["aux"][4:], o["aux"][:4] * o["aux"][:4])
 
 
+@pytest.mark.parametrize("basis_dim", [1, 4, 16, 25])
+def test_oracle_other_sh_orders_match_live_reference_cpu(oracle, poses8, basis_dim):
+    """The reference supports SH1/4/9/16/25 (lumisphere.hpp:38-81); the shipped scenes use SH9.  Pin the other orders too."""
+    if oracle.ref_cpu_lib() is None:
+        pytest.skip("oracle/_ref/libref_cpu.so not built (needs /root/reference)")
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=6, shell=1.0, halo=0.05, seed=20 + basis_dim, basis_dim=basis_dim)
+    assert int(tree["data_dim"]) == 3 * basis_dim + 1
+    W, H = 80, 64
+    fx = S.blender_focal(W)
+    rng = oracle.frame_rng(4)
+    ref = oracle.ref_cpu_render(tree, poses8[4], W, H, fx, fx, 6, rng)
+    o = oracle.render(tree, poses8[4], W, H, fx, fx, 6, rng)
+    assert o["aux"][3].max() == 1.0
+    assert np.array_equal(o["aux"][3], ref[3])
+    assert np.abs(o["aux"] - ref).max() <= 1e-6
+
+
 def test_unsupported_spp_raises(oracle, small_tree, poses8):
     with pytest.raises(ValueError, match="spp == 5 not supported"):
         oracle.render(small_tree, poses8[0], 8, 8, 100.0, 100.0, 5, oracle.frame_rng(0))

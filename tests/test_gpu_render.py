@@ -195,6 +195,61 @@ def test_frame_rng_is_pure_function_of_frame(capi, mid_tree, poses8):
         assert np.array_equal(ctx.read_aux(), seq[f])
 
 
+@pytest.mark.parametrize("size", [(67, 45), (13, 7), (1, 1), (8, 4), (17, 129)])
+def test_ragged_image_sizes(capi, oracle, small_tree, poses8, size):
+    """Image sizes that are not multiples of the 16x8 super-tile / 8x4 warp tile (partially filled tiles, a single pixel):
+    both kernels bit-exact against the oracle, nothing written outside the image."""
+    from rt_octree_b200 import synthetic as S
+
+    W, H = size
+    fx = S.blender_focal(max(W, 64)) * 0.5
+    t, ctx, cam = _setup(capi, small_tree, W, H, fx)
+    cam.transform = poses8[1]
+    for spp, denoise in ((6, False), (1, True)):
+        ctx.rng_set_frame(1)
+        capi.launch_renderer(t, cam, _opts(capi, spp, denoise=denoise), ctx)          # brick-grid kernel
+        aux_grid = ctx.read_aux().copy()
+        tr = GpuTrace(capi, W * H, spp)
+        capi.launch_renderer(t, cam, _opts(capi, spp, denoise=denoise), ctx, trace=tr.pod)
+        g = tr.host()
+        assert np.array_equal(ctx.read_aux(), aux_grid)
+        o = oracle.render(small_tree, poses8[1], W, H, fx, fx, spp, oracle.frame_rng(1), thresh=g["thresh"], want_img=True)
+        for k in TRACE_KEYS:
+            assert np.array_equal(g[k], o[k]), k
+        assert np.array_equal(aux_grid[3], o["aux"][3]) and np.abs(aux_grid - o["aux"]).max() < 1e-5
+        if not denoise:
+            assert np.abs(ctx.read_image() - o["img"]).max() < 1e-5
+
+
+def test_root_only_trees(capi, oracle, poses8):
+    """A one-node tree (8 leaves, depth 1: no brick grid, the production kernel walks the tree), all empty and all dense."""
+    for sigma in (0.0, 50.0):
+        data = np.zeros((1, 2, 2, 2, 28), np.float16)
+        data[..., -1] = sigma
+        data[..., 0] = 0.5
+        tree = {"data_dim": np.int64(28), "data_format": np.array("SH9"), "invradius3": np.full(3, 0.375, np.float32),
+                "offset": np.full(3, 0.5, np.float32), "child": np.zeros((1, 2, 2, 2), np.int32), "data": data}
+        W, H, spp = 24, 24, 4
+        t, ctx, cam = _setup(capi, tree, W, H, 60.0)
+        assert t.info.max_depth == 1 and t.info.grid_level == 0 and t.info.n_leaves == 8
+        cam.transform = poses8[0]
+        ctx.rng_set_frame(0)
+        capi.launch_renderer(t, cam, _opts(capi, spp), ctx)
+        aux = ctx.read_aux().copy()
+        tr = GpuTrace(capi, W * H, spp)
+        capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)
+        g = tr.host()
+        assert np.array_equal(ctx.read_aux(), aux)
+        o = oracle.render(tree, poses8[0], W, H, 60.0, 60.0, spp, oracle.frame_rng(0), thresh=g["thresh"])
+        for k in TRACE_KEYS:
+            assert np.array_equal(g[k], o[k]), k
+        assert np.array_equal(aux[3], o["aux"][3]) and np.abs(aux - o["aux"]).max() < 1e-5
+        if sigma == 0.0:
+            assert aux[3].max() == 0.0 and np.all(aux[:3] == 1.0)   # pure background
+        else:
+            assert aux[3].max() == 1.0
+
+
 def test_errors(capi, small_tree):
     t, ctx, cam = _setup(capi, small_tree, 32, 32, 40.0)
     o = _opts(capi, 6)

@@ -32,11 +32,24 @@ def build():
     return lib
 
 
-def frame_rng(frame, warmup=100):
-    """pcg32(20230418) advanced by (warmup + frame) * 2^32 (oracle/oracle.py::frame_rng without the oracle import)."""
-    from oracle import oracle as O
-
-    return O.frame_rng(frame)
+def frame_rng(frame, warmup=100, seed=20230418):
+    """ctx.rng when the headless driver renders pose `frame`: pcg32(seed) advanced by (warmup + frame) * 2^32
+    (pcg32.h:53-59,145-166; stated here in plain Python so that the tool does not touch oracle/)."""
+    M, MASK = 6364136223846793005, (1 << 64) - 1
+    inc = 3                                         # (initseq = 1) << 1 | 1
+    state = (0 * M + inc) & MASK                    # first next() on state 0
+    state = (state + seed) & MASK
+    state = (state * M + inc) & MASK
+    delta = ((warmup + frame) << 32) & MASK
+    cur_mult, cur_plus, acc_mult, acc_plus = M, inc, 1, 0
+    while delta > 0:
+        if delta & 1:
+            acc_mult = (acc_mult * cur_mult) & MASK
+            acc_plus = (acc_plus * cur_mult + cur_plus) & MASK
+        cur_plus = ((cur_mult + 1) * cur_plus) & MASK
+        cur_mult = (cur_mult * cur_mult) & MASK
+        delta >>= 1
+    return (acc_mult * state + acc_plus) & MASK, inc
 
 
 def main():

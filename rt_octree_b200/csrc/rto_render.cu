@@ -3,11 +3,13 @@
 // One launch replaces the reference's render_kernel<SPP> (renderer/src/cuda/volrend.cu:84-213) and everything it
 // inlines (rt_core.cuh:195-332, n3tree_query.hpp:13-48, lumisphere.hpp:38-81, pcg32.h).  Design:
 //   * a warp owns an 8x4 pixel tile (the reference maps 32 consecutive x to a warp) => coherent rays per warp,
-//     aux/image rows written as full 32 B sectors;
-//   * node words (child pointer | leaf flag + sigma) are 32 B per node, one sector;
-//   * per-ray ancestor stack in shared memory, integer-coordinate descent resumed at the common ancestor
-//     (rto_ray.cuh) instead of a root restart per step;
-//   * thresholds, hit list and counts live in registers for SPP <= 8 (the reference keeps them in local memory);
+//     aux/image rows written as full 32 B sectors; persistent blocks claim 16x8 super-tiles from a global counter;
+//   * production marching loop (GRID = 2): sparse brick grid, one table load + one BYTE load per step (depth | dense flag),
+//     the 4-byte leaf word (sigma) only in cells with non-zero sigma; GRID = 1 reads the leaf words on every step;
+//   * tree walker (GRID = 0; trace builds, trees without a grid): per-ray ancestor stack in shared memory, integer-coordinate
+//     descent resumed at the common ancestor (rto_ray.cuh) instead of a root restart per step;
+//   * thresholds, hit list, counts and the optical-depth state live in per-ray shared-memory scratch (the reference keeps
+//     them in 176 B of local memory per thread);
 //   * SH payload is a separate fp16 plane padded to 64 B per leaf and is touched only for collided leaves.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

@@ -170,7 +170,7 @@ int rto_render_trace(rto_context* ctx, const rto_tree* tree, const rto_camera* c
 
 /* ---- denoiser : Denoiser(ts_module_path) / Denoiser::denoise(cam, ctx, stream)  (src/denoiser/denoiser.cpp:8-71)
  * Weights are the four fp16 tensors of the deployed GuidanceNet (network.py:123-168), exported once from the
- * reference's ts_*.ts by tools/export_guidance_net.py: w1 [mid][in][3][3], b1 [mid], w2 [2L][mid][3][3], b2 [2L]. */
+ * reference's ts_*.ts by tools/make_ts_module.py --export: w1 [mid][in][3][3], b1 [mid], w2 [2L][mid][3][3], b2 [2L]. */
 int rto_net_create(rto_net** out, const void* w1_f16, const void* b1_f16, const void* w2_f16, const void* b2_f16,
                    int in_ch, int mid_ch, int levels);
 void rto_net_destroy(rto_net* net);

@@ -454,7 +454,7 @@ def launch_renderer(tree: N3Tree, cam: Camera, options: RenderOptions, ctx: Rend
 # ---------------------------------------------------------------------------------------------------- Denoiser
 class Denoiser:
     """volrend::Denoiser (denoiser.hpp:11-21).  The reference loads a TorchScript file; here the same four fp16
-    tensors are read from the raw export made once by tools/export_guidance_net.py (`<name>.npz` with w1,b1,w2,b2)
+    tensors are read from the raw export made once by tools/make_ts_module.py --export (`<name>.npz` with w1,b1,w2,b2)
     or passed as arrays.  An empty path raises, like the reference (denoiser.cpp:13-16)."""
 
     def __init__(self, weights):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RTO_ABI_VERSION 1
+#define RTO_ABI_VERSION 2
 
 typedef enum rto_status {
     RTO_OK = 0,
@@ -92,6 +92,11 @@ typedef struct rto_trace {
     int32_t* leaf_seq;    /* [n][max_seq] */
     float* thresh;        /* [n][spp] sorted thresholds dst[] (lg2.approx based) */
     int max_seq;
+    int marcher;          /* which marching loop writes the record: 0 = tree walker (ancestor-stack descent),
+                             1 = the PRODUCTION brick-grid marcher (the loop rto_render runs; the leaf visited at every step
+                             is located through the tree as well, which also cross-checks the grid's depth and sigma: a
+                             disagreement is reported as term = -777).  Trees without a brick grid (depth < 4 or > 11) are
+                             marched by the tree walker in both modes, exactly like rto_render does. */
 } rto_trace;
 
 const char* rto_last_error(void);
@@ -155,16 +160,27 @@ int rto_context_read_image(rto_context* ctx, float* host_dst, void* stream);
 /* the same image as RGBA8 [H][W][4], converted on the device exactly like the reference CLI converts on the host before
  * writing a PNG, `(uint8_t)(v * 255)` (main_headless.cpp:524-541): a quarter of the device->host bytes */
 int rto_context_read_image_rgba8(rto_context* ctx, unsigned char* host_dst, void* stream);
+/* device pointer of that RGBA8 copy ([H][W][4] bytes; allocated by the first call).  Once it exists, the kernels that produce
+ * the image (rto_render with denoise off, rto_denoise's filter) write it from the same epilogue, so the read-back above
+ * costs no extra launch. */
+unsigned char* rto_context_image_rgba8(rto_context* ctx);
 
 /* ---- render : volrend::launch_renderer(tree, cam, options, ctx, stream, offscreen=true)
- *               include/volrend/cuda/renderer_kernel.hpp:11-16, src/cuda/volrend.cu:236-285 ---- */
+ *               include/volrend/cuda/renderer_kernel.hpp:11-16, src/cuda/volrend.cu:236-285 ----
+ * CONTRACT (multi-stream callers): a context carries the work counter of the persistent render kernel and the frame's
+ * buffers, so at most ONE render / denoise may be in flight per context; pipelined callers use one context per stream
+ * (the reference has a single RenderContext and a single blocking stream, main_headless.cpp:441-447).  Trees and nets are
+ * read-only and may be shared by any number of contexts, streams and host threads of the same device.
+ * SIDE EFFECT: the first render of a tree with a brick grid raises the DEVICE limit cudaLimitPersistingL2CacheSize to the
+ * size of the plane the marching loop reads (16 MB for the bench tree; never lowered) so that the per-frame streaming
+ * buffers cannot evict it from L2; RTO_L2_PERSIST=0 in the environment disables this. */
 int rto_render(rto_context* ctx, const rto_tree* tree, const rto_camera* cam, const rto_render_options* opt,
                void* stream);
 /* Same, restricted to the pixel rectangle [x0,x1) x [y0,y1) (single-frame tile split); pixel
  * indices, RNG offsets and buffer addresses stay full-frame. */
 int rto_render_rect(rto_context* ctx, const rto_tree* tree, const rto_camera* cam, const rto_render_options* opt,
                     int x0, int y0, int x1, int y1, void* stream);
-/* Same kernel with the per-ray traversal record switched on (parity tests only). */
+/* Same kernel with the per-ray traversal record switched on (parity tests only); trace->marcher selects the loop. */
 int rto_render_trace(rto_context* ctx, const rto_tree* tree, const rto_camera* cam, const rto_render_options* opt,
                      const rto_trace* trace, void* stream);
 
@@ -202,6 +218,31 @@ int rto_filter_forward_save(const float* weight_dev, const float* guidance_dev, 
 int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, const float* weight_dev, const float* guidance_dev,
                         const float* rgb_filtered_dev, const float* max_map_dev, const float* inv_kernel_sum_dev, int levels,
                         int width, int height, float* grad_weight_dev, float* grad_guidance_dev, void* stream);
+
+/* ---- pipelined callers (no counterpart in the reference, whose driver owns one blocking stream, main_headless.cpp:445) ----
+ * Non-blocking streams and pinned host memory without linking the CUDA runtime into the host program. */
+int rto_stream_create(void** stream);
+int rto_stream_destroy(void* stream);
+int rto_host_alloc(void** ptr, size_t bytes);   /* cudaHostAlloc: destinations of asynchronous read-backs */
+int rto_host_free(void* ptr);
+
+/* One frame of the path — launch_renderer, Denoiser::denoise and the read-backs of main_headless.cpp:506-541 — captured once
+ * as a CUDA graph on `ctx` and replayed with ONE launch per frame.  Per frame only the camera transform and ctx.rng (the state
+ * rto_context_rng_* left at the time of the call) change; tree, net, options, focal lengths and the optional PINNED host
+ * destinations (rto_host_alloc; NULL = no copy) are fixed at creation.  Same kernels, same results as the separate calls. */
+typedef struct rto_frame rto_frame;
+typedef struct rto_frame_desc {
+    const rto_tree* tree;
+    const rto_net* net;            /* may be NULL when opt.denoise == 0 */
+    rto_render_options opt;
+    float fx, fy;
+    unsigned char* host_rgba8;     /* [H][W][4] u8   (rto_context_read_image_rgba8) */
+    float* host_image;             /* [H][W][4] f32  (rto_context_read_image) */
+    float* host_aux;               /* [8][H][W] f32  (rto_context_read_aux, the --write_buffer copy) */
+} rto_frame_desc;
+int rto_frame_create(rto_frame** out, rto_context* ctx, const rto_frame_desc* desc);
+int rto_frame_launch(rto_frame* frame, const float c2w[12], void* stream);
+void rto_frame_destroy(rto_frame* frame);
 
 /* ---- timer : RenderContext::Timer (render_context.hpp:122-213) ----
  * With timing enabled rto_render / rto_denoise bracket their launches with cudaEvents on `stream`;

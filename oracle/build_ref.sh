@@ -14,6 +14,7 @@
 #   _denoiser_ref.so   the reference's Python extension (denoiser/extension/bindings.cpp + filtering.cu) as the torch
 #                      extension module `_denoiser_ref`: the unmodified `filtering_autograd` forward + backward
 #   libref_cpu.so      host-compiled reference trace_ray/query/SH functions (oracle/ref_cpu_shim.cpp)
+#   ref_pose_dump      the reference's own _recenter_poses (llff) made callable (oracle/ref_pose_shim.cpp)
 #
 # Two build-time tweaks only (both outside the forward path): `-include cstdint` for imwrite.cpp
 # (gcc 13) and `.type()` -> `.scalar_type()` in the training-backward dispatch of filtering.cu.
@@ -70,6 +71,10 @@ build_cuda_ref() {
   g++ -o "$OUT/volrend_headless" "$OUT/obj/main_headless.o" $LIBOBJ $LINK
   g++ -o "$OUT/ref_driver" "$OUT/obj/ref_driver.o" $LIBOBJ $LINK
   echo "built $OUT/volrend_headless and $OUT/ref_driver"
+  # the reference's own llff pose recentring (anonymous-namespace functions of main_headless.cpp), callable: ref_pose_shim.cpp
+  g++ -std=c++17 -O2 -w $INC -I "$R" -c "$HERE/ref_pose_shim.cpp" -o "$OUT/obj/ref_pose_shim.o"
+  g++ -o "$OUT/ref_pose_dump" "$OUT/obj/ref_pose_shim.o" $LIBOBJ $LINK
+  echo "built $OUT/ref_pose_dump"
   # the reference's own torch extension (what denoiser/network.py:12-46 JIT-builds), under a non-clashing module name
   PYINC="$(python3 -c 'import sysconfig;print(sysconfig.get_paths()["include"])')"
   if newer "$OUT/patched/filtering.cu" "$OUT/_denoiser_ref.so"; then

@@ -46,7 +46,13 @@ class TreeInfoPOD(C.Structure):
 
 class TracePOD(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("steps", "term", "src_bits", "t_bits", "leaf_hash", "depth_sum", "n_hits",
-                                          "n_loads", "hit_leaf", "hit_cnt", "leaf_seq", "thresh")] + [("max_seq", C.c_int)]
+                                          "n_loads", "hit_leaf", "hit_cnt", "leaf_seq", "thresh")] + [("max_seq", C.c_int),
+                                                                                                      ("marcher", C.c_int)]
+
+
+class FrameDescPOD(C.Structure):
+    _fields_ = [("tree", C.c_void_p), ("net", C.c_void_p), ("opt", RenderOptionsPOD), ("fx", C.c_float), ("fy", C.c_float),
+                ("host_rgba8", C.c_void_p), ("host_image", C.c_void_p), ("host_aux", C.c_void_p)]
 
 
 EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py checks the library exports them all)
@@ -57,6 +63,8 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_context_read_image", "rto_render", "rto_render_rect", "rto_render_trace",
     "rto_net_create", "rto_net_destroy", "rto_net_set_impl", "rto_net_set_bias_mode", "rto_denoise", "rto_denoise_rows", "rto_net_forward",
     "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
+    "rto_context_image_rgba8", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
+    "rto_frame_create", "rto_frame_launch", "rto_frame_destroy",
 ]
 
 _lib = None
@@ -115,6 +123,16 @@ def load(path: str = LIB_PATH):
     L.rto_filter.argtypes = [P, P, P, I, I, I, P, P]
     L.rto_filter_forward_save.argtypes = [P, P, P, I, I, I, P, P, P, P, P]
     L.rto_filter_backward.argtypes = [P, P, P, P, P, P, P, I, I, I, P, P, P]
+    L.rto_context_image_rgba8.argtypes = [P]
+    L.rto_context_image_rgba8.restype = P
+    L.rto_stream_create.argtypes = [C.POINTER(P)]
+    L.rto_stream_destroy.argtypes = [P]
+    L.rto_host_alloc.argtypes = [C.POINTER(P), C.c_size_t]
+    L.rto_host_free.argtypes = [P]
+    L.rto_frame_create.argtypes = [C.POINTER(P), P, C.POINTER(FrameDescPOD)]
+    L.rto_frame_launch.argtypes = [P, C.POINTER(C.c_float * 12), P]
+    L.rto_frame_destroy.argtypes = [P]
+    L.rto_frame_destroy.restype = None
     L.rto_timer_enable.argtypes = [P, I]
     L.rto_timer_reset.argtypes = [P]
     L.rto_timer_record.argtypes = [P, I]
@@ -490,6 +508,67 @@ class Denoiser:
     def close(self):
         if self._h:
             load().rto_net_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Pinned host memory from the library (rto_host_alloc) viewed as a numpy array: destination of async read-backs."""
+
+    def __init__(self, shape, dtype):
+        self._p = C.c_void_p()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        _check(load().rto_host_alloc(C.byref(self._p), n))
+        self.array = np.ctypeslib.as_array((C.c_ubyte * n).from_address(self._p.value)).view(dtype).reshape(shape)
+        self.ptr = self._p.value
+
+    def close(self):
+        if self._p:
+            self.array = None
+            load().rto_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def stream_create() -> int:
+    s = C.c_void_p()
+    _check(load().rto_stream_create(C.byref(s)))
+    return s.value
+
+
+def stream_destroy(stream: int):
+    _check(load().rto_stream_destroy(C.c_void_p(stream)))
+
+
+class Frame:
+    """rto_frame: render -> denoise -> read-backs of one context captured as a CUDA graph, one launch per frame.
+    `rgba8` / `image` / `aux` are optional PinnedBuffer destinations written by every launch."""
+
+    def __init__(self, ctx: RenderContext, tree: N3Tree, net, options: RenderOptions, fx, fy, rgba8=None, image=None, aux=None):
+        self._h = C.c_void_p()
+        self._keep = (ctx, tree, net, rgba8, image, aux)
+        d = FrameDescPOD(tree._h, net._h if net is not None else None, options.pod(), float(fx), float(fy),
+                         rgba8.ptr if rgba8 is not None else None, image.ptr if image is not None else None,
+                         aux.ptr if aux is not None else None)
+        _check(load().rto_frame_create(C.byref(self._h), ctx._h, C.byref(d)))
+
+    def launch(self, c2w12, stream=0):
+        m = (C.c_float * 12)(*[float(v) for v in np.asarray(c2w12, np.float32).reshape(12)])
+        _check(load().rto_frame_launch(self._h, C.byref(m), C.c_void_p(stream)))
+
+    def close(self):
+        if self._h:
+            load().rto_frame_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

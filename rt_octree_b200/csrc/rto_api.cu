@@ -18,7 +18,7 @@
 namespace rto {
 cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream);
 cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
-                               float4* out, cudaStream_t stream);
+                               float4* out, uchar4* out8, cudaStream_t stream);
 size_t denoise_tc_packed_bytes();
 cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream);
 }  // namespace rto
@@ -38,13 +38,18 @@ struct rto_context {
     int W = 0, H = 0;
     float* aux = nullptr;
     float4* img = nullptr;
-    uchar4* img8 = nullptr;         // RGBA8 copy of img, allocated on first rto_context_read_image_rgba8
+    uchar4* img8 = nullptr;         // RGBA8 copy of img, allocated on first use; once it exists the kernels that produce img
+                                    // (render with denoise off, separable filter) write it in the same epilogue
+    uint64_t img_gen = 0, img8_gen = 0;   // host-side generation of img / of the RGBA8 copy (equal: img8 is current)
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
     int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
     rto::AdvanceMap* adv = nullptr;  // [H + W] pcg32 jump-ahead tables for (adv_spp, adv_inc)
+    rto::AdvanceMap* adv_host = nullptr;   // pinned staging copy: the upload is an async copy on the render stream
+    cudaEvent_t adv_copied = nullptr;      // completion of the last table upload (the staging buffer is reused)
     int adv_spp = 0;
     uint64_t adv_inc = 0;
+    bool capturing = false;                // inside rto_frame_create's stream capture: no timer events
     rto::Pcg32 rng{};
     // Timer
     bool timing = false;
@@ -103,12 +108,12 @@ int check_opt(const rto_render_options* opt) {
 }
 
 void timer_start(rto_context* c, int i, cudaStream_t s) {
-    if (!c->timing) return;
+    if (!c->timing || c->capturing) return;
     c->timer_stream = s;
     cudaEventRecord(c->ev_start[i], s);
 }
 void timer_stop(rto_context* c, int i, cudaStream_t s) {
-    if (!c->timing) return;
+    if (!c->timing || c->capturing) return;
     cudaEventRecord(c->ev_stop[i], s);
     c->ev_used[i] = true;
 }
@@ -280,6 +285,8 @@ int rto_context_create(rto_context** out, int W, int H) {
     if (e == cudaSuccess) e = cudaMalloc(&c->weight_map, px * 6 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->guidance_map, px * 6 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->adv, (size_t)(W + H) * sizeof(rto::AdvanceMap));
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->adv_host, (size_t)(W + H) * sizeof(rto::AdvanceMap), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->adv_copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&c->tile_counter, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(c->tile_counter, 0, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(c->aux, 0, px * 8 * sizeof(float));
@@ -299,6 +306,8 @@ int rto_context_create(rto_context** out, int W, int H) {
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
     cudaFree(c->aux); cudaFree(c->img); cudaFree(c->img8); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
+    if (c->adv_host) cudaFreeHost(c->adv_host);
+    if (c->adv_copied) cudaEventDestroy(c->adv_copied);
     for (int i = 0; i < 3; ++i) {
         if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
         if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
@@ -344,20 +353,50 @@ int rto_context_read_image(rto_context* c, float* dst, void* stream) {
     RTO_CUDA(cudaMemcpyAsync(dst, c->img, (size_t)c->W * c->H * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return RTO_OK;
 }
-int rto_context_read_image_rgba8(rto_context* c, unsigned char* dst, void* stream) {
-    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
-    const size_t n = (size_t)c->W * c->H;
-    if (!c->img8) RTO_CUDA(cudaMalloc(&c->img8, n * sizeof(uchar4)));
-    cudaError_t e = rto::launch_rgba8(c->img, c->img8, n, (cudaStream_t)stream);
+static int ensure_img8(rto_context* c) {
+    if (c->img8) return RTO_OK;
+    RTO_CUDA(cudaMalloc(&c->img8, (size_t)c->W * c->H * sizeof(uchar4)));
+    return RTO_OK;
+}
+// make the RGBA8 copy current on `stream` (no-op when the kernel that produced the image wrote it already)
+static int refresh_img8(rto_context* c, cudaStream_t s) {
+    if (int rc = ensure_img8(c)) return rc;
+    if (c->img8_gen == c->img_gen && c->img_gen != 0) return RTO_OK;
+    cudaError_t e = rto::launch_rgba8(c->img, c->img8, (size_t)c->W * c->H, s);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "rgba8 launch: %s", cudaGetErrorString(e));
     ++g_launches;
-    RTO_CUDA(cudaMemcpyAsync(dst, c->img8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    c->img8_gen = c->img_gen;
     return RTO_OK;
+}
+int rto_context_read_image_rgba8(rto_context* c, unsigned char* dst, void* stream) {
+    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    if (int rc = refresh_img8(c, (cudaStream_t)stream)) return rc;
+    RTO_CUDA(cudaMemcpyAsync(dst, c->img8, (size_t)c->W * c->H * sizeof(uchar4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RTO_OK;
+}
+unsigned char* rto_context_image_rgba8(rto_context* c) {
+    if (!c || ensure_img8(c) != RTO_OK) return nullptr;
+    return reinterpret_cast<unsigned char*>(c->img8);
 }
 
 // --------------------------------------------------------------------------------------------------- render
-static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt,
-                       int x0, int y0, int x1, int y1, const rto_trace* trace, void* stream) {
+// (re)build the pcg32 jump-ahead tables when (W, spp, inc) changed: host arithmetic into the context's pinned staging
+// buffer, then an ASYNC copy on the render stream (stream-ordered before the launch that needs it; no device-wide sync).
+static int ensure_adv_tables(rto_context* c, int spp, cudaStream_t s) {
+    if (c->adv_spp == spp && c->adv_inc == c->rng.inc) return RTO_OK;
+    RTO_CUDA(cudaEventSynchronize(c->adv_copied));   // the previous upload (if any) has finished reading the staging buffer
+    for (int y = 0; y < c->H; ++y) c->adv_host[y] = rto::pcg32_advance_map(c->rng.inc, (uint64_t)y * (uint64_t)c->W * (uint64_t)spp);
+    for (int x = 0; x < c->W; ++x) c->adv_host[(size_t)c->H + x] = rto::pcg32_advance_map(c->rng.inc, (uint64_t)x * (uint64_t)spp);
+    RTO_CUDA(cudaMemcpyAsync(c->adv, c->adv_host, ((size_t)c->H + c->W) * sizeof(rto::AdvanceMap), cudaMemcpyHostToDevice, s));
+    RTO_CUDA(cudaEventRecord(c->adv_copied, s));
+    c->adv_spp = spp;
+    c->adv_inc = c->rng.inc;
+    return RTO_OK;
+}
+
+// everything render_kernel needs for one frame, from the handles and PODs of the C ABI
+static int fill_render_args(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt,
+                            int x0, int y0, int x1, int y1, const rto_trace* trace, rto::RenderArgs& a) {
     if (!c || !t || !cam) return fail(RTO_ERR_INVALID, "NULL argument");
     int rc = check_opt(opt);
     if (rc != RTO_OK) return rc;
@@ -365,7 +404,7 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
         return fail(RTO_ERR_INVALID, "camera %dx%d does not match context %dx%d", cam->width, cam->height, c->W, c->H);
     x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
     x1 = x1 > c->W ? c->W : x1; y1 = y1 > c->H ? c->H : y1;
-    rto::RenderArgs a{};
+    a = rto::RenderArgs{};
     rto::FrameParams& fp = a.fp;
     memcpy(fp.c2w, cam->c2w, sizeof fp.c2w);
     for (int i = 0; i < 3; ++i) { fp.offset[i] = t->info.offset[i]; fp.scale[i] = t->info.scale[i]; }
@@ -379,34 +418,38 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;
     a.tile_counter = c->tile_counter;
-    if (c->adv_spp != opt->spp || c->adv_inc != c->rng.inc) {   // (re)build the jump-ahead tables: depends on W, spp, inc only
-        std::vector<rto::AdvanceMap> tab((size_t)c->H + c->W);
-        for (int y = 0; y < c->H; ++y) tab[y] = rto::pcg32_advance_map(c->rng.inc, (uint64_t)y * (uint64_t)c->W * (uint64_t)opt->spp);
-        for (int x = 0; x < c->W; ++x) tab[(size_t)c->H + x] = rto::pcg32_advance_map(c->rng.inc, (uint64_t)x * (uint64_t)opt->spp);
-        // stream-ordered w.r.t. earlier launches on the legacy stream semantics: plain synchronous copy (rare)
-        RTO_CUDA(cudaDeviceSynchronize());
-        RTO_CUDA(cudaMemcpy(c->adv, tab.data(), tab.size() * sizeof(rto::AdvanceMap), cudaMemcpyHostToDevice));
-        c->adv_spp = opt->spp;
-        c->adv_inc = c->rng.inc;
-    }
     a.adv_rows = c->adv;
     a.adv_cols = c->adv + c->H;
     // with the denoiser on, the final image comes from rto_denoise; the reference then renders into a separate
     // noisy surface whose rgb equals aux channels 0..2 (volrend.cu:188-192 vs :205-212), so nothing is lost here
     a.img = opt->denoise ? nullptr : c->img;
+    a.img8 = opt->denoise ? nullptr : c->img8;   // RGBA8 copy in the same store once a caller has asked for it
     if (trace) {
         a.tr = rto::TraceOut{trace->steps, trace->term, trace->src_bits, trace->t_bits, trace->leaf_hash,
                              trace->depth_sum, trace->n_hits, trace->n_loads, trace->hit_leaf, trace->hit_cnt,
                              trace->leaf_seq, trace->thresh, trace->max_seq};
     }
+    return RTO_OK;
+}
+
+static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt,
+                       int x0, int y0, int x1, int y1, const rto_trace* trace, void* stream) {
+    rto::RenderArgs a;
+    int rc = fill_render_args(c, t, cam, opt, x0, y0, x1, y1, trace, a);
+    if (rc != RTO_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = ensure_adv_tables(c, opt->spp, s)) != RTO_OK) return rc;
     timer_start(c, 0, s);
     bool bad_spp = false;
-    cudaError_t e = rto::launch_render(a, opt->spp, trace != nullptr, s, &bad_spp);
+    cudaError_t e = rto::launch_render(a, opt->spp, trace ? (trace->marcher == 1 ? 2 : 1) : 0, s, &bad_spp);
     timer_stop(c, 0, s);
     if (bad_spp) return fail(RTO_ERR_UNSUPPORTED, "spp == %d not supported.", opt->spp);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
     ++g_launches;
+    if (a.img) {   // a full-frame or band render produced (part of) a new image
+        ++c->img_gen;
+        if (a.img8 && x0 <= 0 && y0 <= 0 && x1 >= c->W && y1 >= c->H) c->img8_gen = c->img_gen;
+    }
     return RTO_OK;
 }
 int rto_render(rto_context* c, const rto_tree* t, const rto_camera* cam, const rto_render_options* opt, void* stream) {
@@ -487,13 +530,15 @@ int rto_denoise_rows(rto_context* c, const rto_net* n, int y0, int y1, void* str
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch (%s): %s", tc ? "tcgen05" : "simt", cudaGetErrorString(e));
     timer_start(c, 2, s);
     if (tc)   // guidance is relu6-bounded here, so the precomputed-exp filter applies
-        e = rto::launch_filter_fast(c->aux, c->weight_map, c->guidance_map, c->W, c->H, y0, y1, c->img, s);
+        e = rto::launch_filter_fast(c->aux, c->weight_map, c->guidance_map, c->W, c->H, y0, y1, c->img, c->img8, s);
     else
         e = rto::launch_filter_simt(c->aux, (size_t)c->W * c->H, 1, c->weight_map, c->guidance_map, L, c->W, c->H, y0, y1,
                                     c->img, s);
     timer_stop(c, 2, s);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
     g_launches += 2;
+    ++c->img_gen;
+    if (tc && c->img8 && y0 <= 0 && y1 >= c->H) c->img8_gen = c->img_gen;   // the filter wrote the RGBA8 copy as well
     return RTO_OK;
 }
 int rto_denoise(rto_context* c, const rto_net* n, void* stream) {
@@ -555,6 +600,150 @@ int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, c
     return RTO_OK;
 }
 
+
+// ------------------------------------------------------------------------------- streams, pinned memory, frame graph
+int rto_stream_create(void** stream) {
+    if (!stream) return fail(RTO_ERR_INVALID, "stream is NULL");
+    cudaStream_t s = nullptr;
+    RTO_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void*)s;
+    return RTO_OK;
+}
+int rto_stream_destroy(void* stream) {
+    if (stream) RTO_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return RTO_OK;
+}
+int rto_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(RTO_ERR_INVALID, "ptr is NULL");
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RTO_ERR_NOMEM : RTO_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return RTO_OK;
+}
+int rto_host_free(void* ptr) {
+    if (ptr) RTO_CUDA(cudaFreeHost(ptr));
+    return RTO_OK;
+}
+
+}  // extern "C"
+
+// One frame of the hot path as an instantiated CUDA graph: render -> GuidanceNet -> filter (+RGBA8) -> device->host copies.
+// The graph is captured once from the very launches rto_render / rto_denoise / rto_context_read_* make; per frame only the
+// render kernel's by-value argument block (camera transform, rng state) is replaced (cudaGraphExecKernelNodeSetParams) and
+// the whole frame goes to the GPU with ONE cudaGraphLaunch.
+struct rto_frame {
+    rto_context* ctx = nullptr;
+    const rto_tree* tree = nullptr;
+    const rto_net* net = nullptr;
+    rto_render_options opt{};
+    rto_camera cam{};
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t render_node = nullptr;
+    cudaKernelNodeParams kp{};
+    rto::RenderArgs args{};
+    void* kparams[1] = {nullptr};
+    int launches_per_frame = 0;
+};
+
+extern "C" {
+
+int rto_frame_create(rto_frame** out, rto_context* c, const rto_frame_desc* d) {
+    if (!out || !c || !d || !d->tree) return fail(RTO_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (int rc = check_opt(&d->opt)) return rc;
+    if (d->opt.denoise && !d->net) return fail(RTO_ERR_INVALID, "options.denoise is set but no net was given");
+    rto_frame* f = new (std::nothrow) rto_frame;
+    if (!f) return fail(RTO_ERR_NOMEM, "out of host memory");
+    f->ctx = c; f->tree = d->tree; f->net = d->net; f->opt = d->opt;
+    f->cam.width = c->W; f->cam.height = c->H; f->cam.fx = d->fx; f->cam.fy = d->fy;
+    for (int i = 0; i < 12; ++i) f->cam.c2w[i] = 0.f;   // identity rotation at the origin; replaced at every launch
+    f->cam.c2w[0] = f->cam.c2w[4] = f->cam.c2w[8] = 1.f;
+    cudaStream_t cap = nullptr;
+    int rc = RTO_OK;
+    auto body = [&](cudaStream_t s) -> int {
+        int r = render_impl(c, d->tree, &f->cam, &d->opt, 0, 0, c->W, c->H, nullptr, s);
+        if (r == RTO_OK && d->opt.denoise) r = rto_denoise(c, d->net, s);
+        if (r == RTO_OK && d->host_rgba8) r = rto_context_read_image_rgba8(c, d->host_rgba8, s);
+        if (r == RTO_OK && d->host_image) r = rto_context_read_image(c, d->host_image, s);
+        if (r == RTO_OK && d->host_aux) r = rto_context_read_aux(c, d->host_aux, s);
+        return r;
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete f; return fail(RTO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    // 1. one uncaptured frame: runs every lazy initialisation (function attributes, L2 set-aside, jump-ahead tables, the
+    //    RGBA8 buffer) that is not allowed inside a capture, and validates the arguments with ordinary error reporting
+    if (d->host_rgba8) rc = ensure_img8(c);
+    if (rc == RTO_OK) rc = body(cap);
+    if (rc == RTO_OK && cudaStreamSynchronize(cap) != cudaSuccess) rc = fail(RTO_ERR_CUDA, "frame warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // 2. the same calls again, captured
+    if (rc == RTO_OK) {
+        const int64_t l0 = g_launches.load();
+        e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) rc = fail(RTO_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+        if (rc == RTO_OK) {
+            c->capturing = true;
+            rc = body(cap);
+            c->capturing = false;
+            e = cudaStreamEndCapture(cap, &f->graph);
+            if (rc == RTO_OK && e != cudaSuccess) rc = fail(RTO_ERR_CUDA, "cudaStreamEndCapture: %s (host destinations must be pinned: rto_host_alloc)", cudaGetErrorString(e));
+        }
+        f->launches_per_frame = (int)(g_launches.load() - l0);
+        g_launches -= f->launches_per_frame;   // captured, not launched
+    }
+    if (rc == RTO_OK) {
+        e = cudaGraphInstantiate(&f->exec, f->graph, 0);
+        if (e != cudaSuccess) rc = fail(RTO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    if (rc == RTO_OK) {   // the render kernel is the only root of the (linear) graph
+        cudaGraphNode_t roots[4];
+        size_t n = 4;
+        e = cudaGraphGetRootNodes(f->graph, roots, &n);
+        cudaGraphNodeType ty = cudaGraphNodeTypeEmpty;
+        if (e == cudaSuccess && n == 1) e = cudaGraphNodeGetType(roots[0], &ty);
+        if (e != cudaSuccess || n != 1 || ty != cudaGraphNodeTypeKernel) rc = fail(RTO_ERR_CUDA, "frame graph: unexpected root (%zu roots, type %d): %s", n, (int)ty, cudaGetErrorString(e));
+        else {
+            f->render_node = roots[0];
+            e = cudaGraphKernelNodeGetParams(f->render_node, &f->kp);
+            if (e != cudaSuccess) rc = fail(RTO_ERR_CUDA, "cudaGraphKernelNodeGetParams: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaStreamDestroy(cap);
+    if (rc != RTO_OK) {
+        std::string keep = g_err;
+        rto_frame_destroy(f);
+        g_err = keep;
+        return rc;
+    }
+    f->kparams[0] = &f->args;
+    f->kp.kernelParams = f->kparams;
+    f->kp.extra = nullptr;
+    *out = f;
+    return RTO_OK;
+}
+
+int rto_frame_launch(rto_frame* f, const float c2w[12], void* stream) {
+    if (!f || !c2w) return fail(RTO_ERR_INVALID, "NULL argument");
+    rto_context* c = f->ctx;
+    memcpy(f->cam.c2w, c2w, sizeof f->cam.c2w);
+    if (c->adv_spp != f->opt.spp || c->adv_inc != c->rng.inc)
+        return fail(RTO_ERR_INVALID, "the context's spp / rng stream changed since rto_frame_create; create a new frame");
+    int rc = fill_render_args(c, f->tree, &f->cam, &f->opt, 0, 0, c->W, c->H, nullptr, f->args);
+    if (rc != RTO_OK) return rc;
+    RTO_CUDA(cudaGraphExecKernelNodeSetParams(f->exec, f->render_node, &f->kp));
+    RTO_CUDA(cudaGraphLaunch(f->exec, (cudaStream_t)stream));
+    g_launches += f->launches_per_frame;
+    ++c->img_gen;
+    if (c->img8) c->img8_gen = c->img_gen;
+    return RTO_OK;
+}
+
+void rto_frame_destroy(rto_frame* f) {
+    if (!f) return;
+    if (f->exec) cudaGraphExecDestroy(f->exec);
+    if (f->graph) cudaGraphDestroy(f->graph);
+    delete f;
+}
 
 // ---------------------------------------------------------------------------------------------------- timer
 int rto_timer_enable(rto_context* c, int enable) {

@@ -241,14 +241,13 @@ cudaError_t launch_filter_backward(const float* dout, const float* img_in, const
     return cudaGetLastError();
 }
 
-// float4 image -> RGBA8 with the reference CLI's conversion `(uint8_t)(v * 255)` (main_headless.cpp:534-537): truncation,
-// no clamp, low byte of the integer — so the bytes equal what the reference hands to its PNG writer.
+// float4 image -> RGBA8 (rgba8_of, rto_internal.h): the stand-alone conversion, used when the image was not produced by a
+// kernel that writes the RGBA8 copy itself (render with denoise off and the separable filter both do).
 __global__ void __launch_bounds__(256) rgba8_kernel(const float4* __restrict__ img, uchar4* __restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 v = img[i];
-    out[i] = make_uchar4((unsigned char)(__float2int_rz(__fmul_rn(v.x, 255.f)) & 0xff), (unsigned char)(__float2int_rz(__fmul_rn(v.y, 255.f)) & 0xff),
-                         (unsigned char)(__float2int_rz(__fmul_rn(v.z, 255.f)) & 0xff), (unsigned char)(__float2int_rz(__fmul_rn(v.w, 255.f)) & 0xff));
+    out[i] = rgba8_of(v.x, v.y, v.z, v.w);
 }
 cudaError_t launch_rgba8(const float4* img, uchar4* out, size_t n, cudaStream_t stream) {
     rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(img, out, n);

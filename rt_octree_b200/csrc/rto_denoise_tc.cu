@@ -27,8 +27,10 @@
 // a horizontal and a vertical box sum of e^{g} * (r,g,b,1) (guidance is in [0,6] after relu6, so the reference's
 // max-subtraction is not needed for range).
 #include <cuda_fp16.h>
-#include <cstdlib>
 #include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdlib>
 
 #include <cfloat>
 #include <cstdint>
@@ -513,7 +515,7 @@ __device__ __forceinline__ void filter_pass1(const float* __restrict__ aux, cons
 
 __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float* __restrict__ aux, const float* __restrict__ weight,
                                                                    const float* __restrict__ guidance, int W, int H, int y0,
-                                                                   int y1, float4* __restrict__ out) {
+                                                                   int y1, float4* __restrict__ out, uchar4* __restrict__ out8) {
     using namespace fs;
     extern __shared__ __align__(16) unsigned char fsm[];
     float4* Hs = reinterpret_cast<float4*>(fsm);                  // [4][SROWS][BW], columns swizzled inside groups of 4
@@ -557,14 +559,19 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int gy = by + ty + k;
-            if (gx < W && gy < H && gy < y1) RTO_ST(out + (size_t)gy * W + gx, make_float4(o[k][0], o[k][1], o[k][2], 1.0f));
+            if (gx < W && gy < H && gy < y1) {
+                RTO_ST(out + (size_t)gy * W + gx, make_float4(o[k][0], o[k][1], o[k][2], 1.0f));
+                if (out8) RTO_ST(out8 + (size_t)gy * W + gx, rgba8_of(o[k][0], o[k][1], o[k][2], 1.0f));   // the bytes `-o` writes to the PNG
+            }
         }
     }
 }
 
 template <int TH>
 static cudaError_t launch_net_th(const NetDev& net, const void* packed, const DenoiseArgs& d, int rows, cudaStream_t stream) {
-    static bool attr_set[kMaxDevices] = {};   // per device: the opt-in shared-memory size is a per-device function attribute
+    // per device: the opt-in shared-memory size is a per-device function attribute.  Atomic flags: several host threads may
+    // drive the same device (volrend_headless --gpu_list 0,0); setting the attribute twice is harmless.
+    static std::atomic<bool> attr_set[kMaxDevices] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -585,12 +592,11 @@ static cudaError_t launch_net_th(const NetDev& net, const void* packed, const De
 cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream) {
     const int rows = d.y1 - d.y0;
     if (rows <= 0) return cudaSuccess;
-    static int th = 0;
-    if (th == 0) {
+    static const int th = [] {   // thread-safe one-time initialisation
         const char* v = getenv("RTO_NET_TILE_H");
-        th = v ? atoi(v) : 10;
-        if (th != 8 && th != 10 && th != 12 && th != 14) th = 10;
-    }
+        const int t = v ? atoi(v) : 10;
+        return (t == 8 || t == 10 || t == 12 || t == 14) ? t : 10;
+    }();
     switch (th) {
         case 8: return launch_net_th<8>(net, packed, d, rows, stream);
         case 12: return launch_net_th<12>(net, packed, d, rows, stream);
@@ -600,10 +606,10 @@ cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const 
 }
 
 cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
-                               float4* out, cudaStream_t stream) {
+                               float4* out, uchar4* out8, cudaStream_t stream) {
     const int rows = y1 - y0;
     if (rows <= 0) return cudaSuccess;
-    static bool attr_set[kMaxDevices] = {};
+    static std::atomic<bool> attr_set[kMaxDevices] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -614,7 +620,7 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
         attr_set[dev] = true;
     }
     dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
-    filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out);
+    filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out, out8);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,15 @@ namespace rto {
 
 constexpr int kMaxDevices = 64;   // per-device launch state (function attributes are per device)
 
+// float4 image -> RGBA8 with the reference CLI's conversion `(uint8_t)(v * 255)` (main_headless.cpp:534-537): truncation,
+// no clamp, low byte of the integer — so the bytes equal what the reference hands to its PNG writer.
+#if defined(__CUDACC__)
+__device__ __forceinline__ uchar4 rgba8_of(float r, float g, float b, float a) {
+    return make_uchar4((unsigned char)(__float2int_rz(__fmul_rn(r, 255.f)) & 0xff), (unsigned char)(__float2int_rz(__fmul_rn(g, 255.f)) & 0xff),
+                       (unsigned char)(__float2int_rz(__fmul_rn(b, 255.f)) & 0xff), (unsigned char)(__float2int_rz(__fmul_rn(a, 255.f)) & 0xff));
+}
+#endif
+
 
 // HBM layout of a loaded tree (structure of arrays)
 struct TreeDev {
@@ -57,13 +66,15 @@ struct RenderArgs {
     int x0, y0, x1, y1;            // pixel rectangle to render (full frame, or a band for the tile split)
     float* aux;                    // [8][H][W] fp32
     float4* img;                   // [H][W] float4, may be nullptr
+    uchar4* img8;                  // [H][W] RGBA8 copy of img written by the same store (nullptr: not wanted)
     int* tile_counter;             // [2] device ints owned by the context: next tile, finished warps (self re-arming)
     const AdvanceMap* adv_rows;    // [H] pcg32 jump-ahead maps for iy*W*spp
     const AdvanceMap* adv_cols;    // [W] ... for ix*spp
     TraceOut tr;
 };
 
-cudaError_t launch_render(const RenderArgs& a, int spp, bool trace, cudaStream_t stream, bool* bad_spp);
+// trace: 0 = off, 1 = tree walker with the traversal record, 2 = production brick-grid marcher with the record
+cudaError_t launch_render(const RenderArgs& a, int spp, int trace, cudaStream_t stream, bool* bad_spp);
 
 // GuidanceNet (deployed form) weights on the device, fp16
 struct NetDev {

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "rto_internal.h"
 #include "rto_ray.cuh"
@@ -80,13 +81,14 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
     return true;
 }
 
-// GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent; TRACE builds
-// always use the tree walker because they must report the leaf visited at every step.
+// GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent.
 // GRID: 0 = tree walker, 1 = brick grid read through the 4-byte leaf words, 2 = brick grid read through the byte plane
 // (production; RTO_GRID8=0 selects 1 for A/B runs).
+// TRACE: write the per-ray traversal record (rto_trace).  TRACE && GRID is the PRODUCTION marcher with the record switched
+// on: steps / term / src / t / hits come straight out of walk_grid, and the visited-leaf sequence is produced by locating
+// every sample point in the tree as well (walk_grid<VERIFY>), which also cross-checks the grid's depth and sigma per step.
 template <int SPP, bool TRACE, int GRID>
 __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RENDER_MIN_BLOCKS : 4)) * 4 / kBlockWarps) render_kernel(const __grid_constant__ RenderArgs a) {
-    static_assert(!(TRACE && GRID), "trace builds use the tree walker");
     extern __shared__ uint32_t ray_smem[];
     __shared__ unsigned s_state;
     const int lane = threadIdx.x & 31;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
                 if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
             };
             if constexpr (GRID != 0)
-                walk_grid<SPP, false, GRID == 2>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+                walk_grid<SPP, TRACE, GRID == 2>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             else
                 walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             const uint32_t sh_nums = wo.n_hits;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
                 RTO_ST(q + 6 * SIZE, f_mul(out2, out2)); RTO_ST(q + 7 * SIZE, f_mul(out3, out3));
             }
             if (a.img) RTO_ST(a.img + idx, make_float4(out0, out1, out2, 1.0f));
+            if (a.img8) RTO_ST(a.img8 + idx, rgba8_of(out0, out1, out2, 1.0f));
         }
         __syncwarp();
     }
@@ -255,39 +258,42 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
 // more slowly, and the frame time is bounded below by the LONGEST ray's serial chain, so the optimum
 // is well below the occupancy limit.  RTO_RENDER_BLOCKS_PER_SM overrides the default for tuning.
 static int tuned_blocks_per_sm(int occ_limit) {
-    static int env = -1;
-    if (env < 0) {
+    static const int env = [] {
         const char* e = getenv("RTO_RENDER_BLOCKS_PER_SM");
-        env = e ? atoi(e) : 0;
-    }
+        return e ? atoi(e) : 0;
+    }();
     int want = env > 0 ? env : kDefaultBlocksPerSM;
     return want < occ_limit ? want : occ_limit;
 }
 
 template <int SPP>
-static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stream) {
+static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t stream) {   // trace: 0 off, 1 tree walker, 2 production marcher
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
-    const bool grid_path = !trace && a.tree.grid.K > 0;
+    const bool grid_path = trace != 1 && a.tree.grid.K > 0;
     const char* g8 = getenv("RTO_GRID8");   // read per launch so that one process can A/B the two planes
     const bool grid8 = grid_path && !(g8 && g8[0] == '0') && a.tree.grid.bricks8 != nullptr;
-    const int v = trace ? 1 : (grid_path ? (grid8 ? 3 : 2) : 0);
+    const int v = (trace ? 3 : 0) + (grid_path ? (grid8 ? 2 : 1) : 0);
     const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
-    // Function attributes, occupancy and the L2 set-aside are per DEVICE (the CLI drives one host thread per GPU), so the
-    // cached launch state is indexed by the current device; slots of different devices are never shared between threads.
+    // Function attributes, occupancy and the L2 set-aside are per DEVICE, so the cached launch state is indexed by the
+    // current device; the one-time set-up of a slot runs under that slot's mutex (several host threads may drive the same
+    // device: volrend_headless --gpu_list 0,0, or a pipelined caller with one thread per stream).
     struct DevState {
+        std::mutex mu;
         int num_sms = 0;
-        size_t smem_set[4] = {0, 0, 0, 0};
-        int occ_limit[4] = {0, 0, 0, 0};
+        size_t smem_set[6] = {0, 0, 0, 0, 0, 0};
+        int occ_limit[6] = {0, 0, 0, 0, 0, 0};
         int persist = -1, max_win = 0, max_persist = 0;
+        size_t persist_set = 0;   // current cudaLimitPersistingL2CacheSize this library asked for on the device
     };
     static DevState dev_state[kMaxDevices];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevState& ds = dev_state[dev >= 0 && dev < kMaxDevices ? dev : 0];
-    void (*kern)(RenderArgs) = trace ? render_kernel<SPP, true, 0>
-                               : (grid8 ? render_kernel<SPP, false, 2> : (grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>));
+    void (*kern)(RenderArgs) = trace ? (grid8 ? render_kernel<SPP, true, 2> : (grid_path ? render_kernel<SPP, true, 1> : render_kernel<SPP, true, 0>))
+                                     : (grid8 ? render_kernel<SPP, false, 2> : (grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>));
+    std::unique_lock<std::mutex> lock(ds.mu);
     if (smem > ds.smem_set[v] || ds.occ_limit[v] == 0) {   // first launch on this device, or a deeper tree than any seen before
         if ((e = cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -308,13 +314,28 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         if (ds.persist) {
             cudaDeviceGetAttribute(&ds.max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
             cudaDeviceGetAttribute(&ds.max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-            if (ds.max_persist <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)ds.max_persist) != cudaSuccess) ds.persist = 0;
+            if (ds.max_persist <= 0) ds.persist = 0;
         }
     }
-    if (ds.persist && grid_path && a.tree.grid_brick_bytes > 0) {
-        // the plane the marching loop reads on (almost) every step: the byte bricks when they are in use
-        size_t bytes = grid8 ? a.tree.grid_brick_bytes / sizeof(uint32_t) : a.tree.grid_brick_bytes;
-        if (ds.max_win > 0 && bytes > (size_t)ds.max_win) bytes = (size_t)ds.max_win;
+    const bool use_window = ds.persist && grid_path && a.tree.grid_brick_bytes > 0;
+    // the plane the marching loop reads on (almost) every step: the byte bricks when they are in use
+    size_t bytes = grid8 ? a.tree.grid_brick_bytes / sizeof(uint32_t) : a.tree.grid_brick_bytes;
+    if (use_window) {
+        // L2 set-aside for persisting lines: a process-wide DEVICE limit (documented in rtoctree_b200.h).  It is sized to the
+        // plane it protects, grown only when a larger tree is rendered, never above the device maximum.
+        size_t want = bytes < (size_t)ds.max_persist ? bytes : (size_t)ds.max_persist;
+        want = (want + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        if (want > (size_t)ds.max_persist) want = (size_t)ds.max_persist;
+        if (want > ds.persist_set) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) ds.persist_set = want;
+            else { ds.persist = 0; (void)cudaGetLastError(); }
+        }
+    }
+    const size_t persist_set = ds.persist_set;
+    const int max_win = ds.max_win;
+    lock.unlock();
+    if (use_window && persist_set > 0) {
+        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kBlockThreads);
@@ -324,7 +345,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
         at[0].id = cudaLaunchAttributeAccessPolicyWindow;
         at[0].val.accessPolicyWindow.base_ptr = grid8 ? (void*)const_cast<uint8_t*>(a.tree.grid.bricks8) : (void*)const_cast<uint32_t*>(a.tree.grid.bricks);
         at[0].val.accessPolicyWindow.num_bytes = bytes;
-        at[0].val.accessPolicyWindow.hitRatio = bytes <= (size_t)ds.max_persist ? 1.0f : (float)ds.max_persist / (float)bytes;
+        at[0].val.accessPolicyWindow.hitRatio = bytes <= persist_set ? 1.0f : (float)persist_set / (float)bytes;
         at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = at;
@@ -336,7 +357,7 @@ static cudaError_t launch_spp(const RenderArgs& a, bool trace, cudaStream_t stre
 }
 
 // SPP dispatch = the reference's instantiation list (volrend.cu:266-278); anything else is an error there too.
-cudaError_t launch_render(const RenderArgs& a, int spp, bool trace, cudaStream_t stream, bool* bad_spp) {
+cudaError_t launch_render(const RenderArgs& a, int spp, int trace, cudaStream_t stream, bool* bad_spp) {
     *bad_spp = false;
     switch (spp) {
         case 1: return launch_spp<1>(a, trace, stream);

@@ -5,9 +5,13 @@
 //
 // Same flags (opts.cpp:7-31 + main_headless.cpp:202-223), same pose loaders (:255-370), camera conventions (:372-390),
 // 100-frame warm-up protocol (:469-479), per-pose rng.advance() (:506), `buf_<basename>.bin` layout (:512-523) and timer
-// report (render_context.hpp:190-206).  Additions (all optional): --num_gpus N shards the poses over N GPUs (one host
-// thread + one replica of the tree per GPU, no communication); --warmup K; --write_float also dumps the final float4
-// image as `img_<basename>.bin`; --dry_run parses every input and prints a JSON summary without touching a GPU.
+// report (render_context.hpp:190-206).  Additions (all optional): --num_gpus N / --gpu_list a,b,.. shard the poses over
+// GPUs (one host thread + one replica of the tree per shard, no communication); --pipe N keeps N frames in flight on N
+// (context, stream) pairs, each frame one CUDA-graph launch (--no_graph: separate launches), outputs land in pinned ring
+// buffers and are written by --writers threads; --readback {rgba8,float,aux} copies results to the host every frame even
+// without -o (timing with the device->host copy inside); --warmup K; --write_float also dumps the final float4 image as
+// `img_<basename>.bin`; --dump_poses F; --dry_run parses every input and prints a JSON summary without touching a GPU.
+// Every frame's rng state is a pure function of its global index, so all of these modes write identical files.
 // Differences, on purpose: the tt pose directory is read in sorted order (the reference iterates it unsorted, :282);
 // PNGs are written with zlib directly (the reference needs libpng).
 #include <zlib.h>
@@ -19,10 +23,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <filesystem>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <sstream>
 #include <string>
@@ -51,7 +59,7 @@ struct Args {
 Args parse_args(int argc, char** argv) {
     static const std::map<std::string, std::string> shorts = {{"w", "width"}, {"h", "height"}, {"s", "step_size"}, {"e", "stop_thresh"},
                                                               {"a", "sigma_thresh"}, {"o", "write_images"}, {"i", "intrin"}, {"r", "reverse_yz"}};
-    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float"};
+    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float", "no_graph"};
     Args a;
     for (int k = 1; k < argc; ++k) {
         std::string t = argv[k];
@@ -98,8 +106,14 @@ void print_help() {
          "      --ts_module arg     GuidanceNet weights (npz export of the reference's ts_*.ts)\n"
          "      --write_buffer      save auxiliary buffers (buf_<name>.bin). Invalid if output directory is not given.\n"
          "      --num_gpus arg      shard the poses over this many GPUs (default: 1)\n"
+         "      --gpu_list arg      comma-separated device ids, one shard per entry (e.g. 0,1,2,3; 0,0 = two shards on GPU 0)\n"
+         "      --pipe arg          frames in flight per GPU: N contexts/streams, CUDA-graph frames (default: 1 = reference protocol)\n"
+         "      --no_graph          with --pipe: issue the kernels separately instead of one graph launch per frame\n"
+         "      --readback arg      copy rgba8 | float | aux to pinned host memory every frame even without -o\n"
+         "      --writers arg       file-writer threads used with --pipe (default: 4)\n"
          "      --warmup arg        warm-up frames on pose 0 (default: 100)\n"
          "      --write_float       also save the final float4 image as img_<name>.bin\n"
+         "      --dump_poses arg    write every camera transform (after loader + convention) as float32 [n][12]\n"
          "      --dry_run           parse all inputs, print a JSON summary, do not touch the GPU");
 }
 
@@ -114,31 +128,60 @@ V3 normalize3(V3 v) {   // main_headless.cpp:102-106
 }
 V3 col(const Mat43& t, int c) { return {t.m[c * 3], t.m[c * 3 + 1], t.m[c * 3 + 2]}; }
 
-// general 4x4 inverse (column-major), cofactor expansion in float like glm::inverse
-void inverse4(const float* a, float* inv) {
-    float t[16];
-    t[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
-    t[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
-    t[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
-    t[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
-    t[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
-    t[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
-    t[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
-    t[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
-    t[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
-    t[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
-    t[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
-    t[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
-    t[3] = -a[1] * a[6] * a[11] + a[1] * a[7] * a[10] + a[5] * a[2] * a[11] - a[5] * a[3] * a[10] - a[9] * a[2] * a[7] + a[9] * a[3] * a[6];
-    t[7] = a[0] * a[6] * a[11] - a[0] * a[7] * a[10] - a[4] * a[2] * a[11] + a[4] * a[3] * a[10] + a[8] * a[2] * a[7] - a[8] * a[3] * a[6];
-    t[11] = -a[0] * a[5] * a[11] + a[0] * a[7] * a[9] + a[4] * a[1] * a[11] - a[4] * a[3] * a[9] - a[8] * a[1] * a[7] + a[8] * a[3] * a[5];
-    t[15] = a[0] * a[5] * a[10] - a[0] * a[6] * a[9] - a[4] * a[1] * a[10] + a[4] * a[2] * a[9] + a[8] * a[1] * a[6] - a[8] * a[2] * a[5];
-    const float det = a[0] * t[0] + a[1] * t[4] + a[2] * t[8] + a[3] * t[12];
-    const float id = 1.0f / det;
-    for (int i = 0; i < 16; ++i) inv[i] = t[i] * id;
+// inverse(poses_avg) * pose, in exactly the fp32 operation order of the reference's glm calls, so that the recentred llff
+// poses (and through them every ray) are bit-identical to the reference CLI's:
+//   glm::inverse(mat4)  = detail::compute_inverse<4,4>  (3rdparty/glm/glm/detail/func_matrix.inl:347-405): 18 2x2 sub-
+//                         determinants "Coef", four cofactor columns (a*F - b*F) + c*F, sign flips, the determinant as
+//                         (d.x + d.y) + (d.z + d.w) of column 0 times row 0 of the cofactor matrix, one reciprocal,
+//                         every element multiplied by it;
+//   mat4 * mat4         = ((A0*b0 + A1*b1) + A2*b2) + A3*b3 per column (detail/type_mat4x4.inl:630-648).
+// The reference is built without -ffast-math and without FMA contraction (CMakeLists.txt:30,66: x86-64 baseline), as is this
+// file (host/Makefile): plain IEEE multiplies and adds in source order.  m[c][r] = column c, row r.
+typedef float M4[4][4];
+void inverse4_glm(const M4 m, M4 out) {
+    const float Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3];
+    const float Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
+    const float Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+    const float Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
+    const float Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3];
+    const float Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    const float Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2];
+    const float Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2];
+    const float Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    const float Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
+    const float Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3];
+    const float Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    const float Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2];
+    const float Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2];
+    const float Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+    const float Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+    const float Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1];
+    const float Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+    const float Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+    const float Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+    const float Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+    const float Vec0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]}, Vec1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+    const float Vec2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]}, Vec3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+    static const float SignA[4] = {+1, -1, +1, -1}, SignB[4] = {-1, +1, -1, +1};
+    M4 inv;
+    for (int i = 0; i < 4; ++i) {
+        const float Inv0 = (Vec1[i] * Fac0[i] - Vec2[i] * Fac1[i]) + Vec3[i] * Fac2[i];
+        const float Inv1 = (Vec0[i] * Fac0[i] - Vec2[i] * Fac3[i]) + Vec3[i] * Fac4[i];
+        const float Inv2 = (Vec0[i] * Fac1[i] - Vec1[i] * Fac3[i]) + Vec3[i] * Fac5[i];
+        const float Inv3 = (Vec0[i] * Fac2[i] - Vec1[i] * Fac4[i]) + Vec2[i] * Fac5[i];
+        inv[0][i] = Inv0 * SignA[i];
+        inv[1][i] = Inv1 * SignB[i];
+        inv[2][i] = Inv2 * SignA[i];
+        inv[3][i] = Inv3 * SignB[i];
+    }
+    const float Dot0[4] = {m[0][0] * inv[0][0], m[0][1] * inv[1][0], m[0][2] * inv[2][0], m[0][3] * inv[3][0]};
+    const float Dot1 = (Dot0[0] + Dot0[1]) + (Dot0[2] + Dot0[3]);
+    const float OneOverDeterminant = 1.0f / Dot1;
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) out[c][r] = inv[c][r] * OneOverDeterminant;
 }
 
-// _recenter_poses (main_headless.cpp:152-189): pose <- inverse(poses_avg) * pose
+// _recenter_poses (main_headless.cpp:152-189): pose <- mat4x3(inverse(expand(poses_avg)) * expand(pose))
 void recenter_poses(std::vector<Mat43>& trans) {
     V3 z{0, 0, 0}, up{0, 0, 0}, cen{0, 0, 0};
     for (const Mat43& t : trans) { z = z + col(t, 2); up = up + col(t, 1); cen = cen + col(t, 3); }
@@ -150,17 +193,14 @@ void recenter_poses(std::vector<Mat43>& trans) {
     z = normalize3(z);
     const V3 x = normalize3(cross(up, z));
     const V3 y = normalize3(cross(z, x));
-    float c2w[16] = {x.x, x.y, x.z, 0, y.x, y.y, y.z, 0, z.x, z.y, z.z, 0, cen.x, cen.y, cen.z, 1};
-    float inv[16];
-    inverse4(c2w, inv);
+    const M4 c2w = {{x.x, x.y, x.z, 0.0f}, {y.x, y.y, y.z, 0.0f}, {z.x, z.y, z.z, 0.0f}, {cen.x, cen.y, cen.z, 1.0f}};
+    M4 A;
+    inverse4_glm(c2w, A);
     for (Mat43& p : trans) {
-        float p4[16] = {p.m[0], p.m[1], p.m[2], 0, p.m[3], p.m[4], p.m[5], 0, p.m[6], p.m[7], p.m[8], 0, p.m[9], p.m[10], p.m[11], 1};
+        const M4 B = {{p.m[0], p.m[1], p.m[2], 0.0f}, {p.m[3], p.m[4], p.m[5], 0.0f}, {p.m[6], p.m[7], p.m[8], 0.0f}, {p.m[9], p.m[10], p.m[11], 1.0f}};
         for (int c = 0; c < 4; ++c)
-            for (int r = 0; r < 3; ++r) {
-                float s = 0.f;
-                for (int k = 0; k < 4; ++k) s += inv[k * 4 + r] * p4[c * 4 + k];
-                p.m[c * 3 + r] = s;
-            }
+            for (int r = 0; r < 3; ++r)
+                p.m[c * 3 + r] = ((A[0][r] * B[c][0] + A[1][r] * B[c][1]) + A[2][r] * B[c][2]) + A[3][r] * B[c][3];
     }
 }
 
@@ -235,18 +275,173 @@ uint64_t fnv64(const void* p, size_t n) {
 }
 
 struct Job {
-    std::string tree_path, out_dir, ts_module;
+    std::string tree_path, out_dir, ts_module, readback;
     std::vector<Mat43> trans;
     std::vector<std::string> basenames;
     RenderOptions options;
     int width, height;
     float fx, fy;
-    bool llff, write_buffer, write_float;
-    int warmup;
+    bool llff, write_buffer, write_float, graph;
+    int warmup, pipe, writers;
 };
 
-// one GPU: frames [begin, end) of the job; ms[3]/frames receive this shard's timer sums
-void run_shard(const Job& job, int device, size_t begin, size_t end, float* ms, int* frames, bool verbose) {
+struct ShardStats {
+    float ms[3] = {0.f, 0.f, 0.f};   // mean render / net / filter ms per frame (stage events; serial protocol only)
+    int frames = 0;
+    double wall_s = 0.0;             // wall clock of the timed loop (first launch -> last result on the host)
+    bool staged = false;             // ms[] valid
+};
+
+void write_outputs(const Job& job, size_t i, const float* aux, const uint8_t* rgba8, const float* img) {
+    if (job.write_buffer && aux) {   // main_headless.cpp:512-523
+        std::ofstream out(job.out_dir + "/buf_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
+        out.write(reinterpret_cast<const char*>(aux), (std::streamsize)((size_t)RenderContext::CHANNELS * job.width * job.height * sizeof(float)));
+    } else if (rgba8) {              // main_headless.cpp:524-541
+        write_png_file(job.out_dir + "/" + job.basenames[i] + ".png", rgba8, job.width, job.height);
+    }
+    if (job.write_float && img) {
+        std::ofstream out(job.out_dir + "/img_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
+        out.write(reinterpret_cast<const char*>(img), (std::streamsize)((size_t)4 * job.width * job.height * sizeof(float)));
+    }
+}
+
+// a few threads that turn finished frames into files while the GPU renders the next ones
+class WriterPool {
+   public:
+    explicit WriterPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~WriterPool() {
+        { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> l(mu_); q_.push_back(std::move(f)); }
+        cv_.notify_one();
+    }
+   private:
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> th_;
+    bool stop_ = false;
+};
+
+// one frame slot of the pipeline: its own context + stream (+ graph) and pinned result buffers
+struct Slot {
+    RenderContext ctx;
+    void* stream = nullptr;
+    rto_frame* frame = nullptr;
+    uint8_t* h_rgba8 = nullptr;
+    float* h_img = nullptr;
+    float* h_aux = nullptr;
+    long pending = -1;                 // global index of the frame in flight on this slot
+    std::mutex mu;                     // writer hand-off: `writing` is true while a writer thread reads the pinned buffers
+    std::condition_variable cv;
+    bool writing = false;
+    ~Slot() {
+        rto_frame_destroy(frame);
+        rto_host_free(h_rgba8); rto_host_free(h_img); rto_host_free(h_aux);
+        ctx.freeResource();
+        rto_stream_destroy(stream);
+    }
+};
+
+// --pipe N: N frames in flight.  Frame i runs on slot i % N: wait until the slot's previous frame (and its file writer) are
+// done, then enqueue render -> denoise -> read-backs for pose i without any further host synchronisation.
+void run_shard_pipelined(const Job& job, N3Tree& tree, Denoiser& denoiser, size_t begin, size_t end, ShardStats& st) {
+    const int W = job.width, H = job.height;
+    const size_t px = (size_t)W * H;
+    const bool files = job.out_dir.size() > 0;
+    const bool want_aux = (files && job.write_buffer) || job.readback == "aux";
+    const bool want_rgba8 = (files && !job.write_buffer) || job.readback == "rgba8";
+    const bool want_img = (files && job.write_float) || job.readback == "float";
+    const rto_render_options opt = job.options.pod();
+    std::vector<std::unique_ptr<Slot>> slots;
+    for (int k = 0; k < job.pipe; ++k) {
+        auto s = std::make_unique<Slot>();
+        s->ctx.offscreen = true;
+        s->ctx.update(W, H);
+        rto_check(rto_stream_create(&s->stream), "stream");
+        if (want_rgba8) rto_check(rto_host_alloc(reinterpret_cast<void**>(&s->h_rgba8), px * 4), "pinned rgba8");
+        if (want_img) rto_check(rto_host_alloc(reinterpret_cast<void**>(&s->h_img), px * 16), "pinned image");
+        if (want_aux) rto_check(rto_host_alloc(reinterpret_cast<void**>(&s->h_aux), px * 32), "pinned aux");
+        if (job.graph) {
+            rto_frame_desc d{};
+            d.tree = tree.device; d.net = job.options.denoise ? denoiser.handle() : nullptr; d.opt = opt;
+            d.fx = job.fx; d.fy = job.fy;
+            d.host_rgba8 = s->h_rgba8; d.host_image = s->h_img; d.host_aux = s->h_aux;
+            rto_check(rto_frame_create(&s->frame, s->ctx.handle, &d), "rto_frame_create");
+        }
+        slots.push_back(std::move(s));
+    }
+    rto_camera cam{};
+    cam.width = W; cam.height = H; cam.fx = job.fx; cam.fy = job.fy;
+    auto issue = [&](Slot& s, const Mat43& pose, int64_t warm, int64_t frame) {
+        rto_check(rto_context_rng_set_frame(s.ctx.handle, warm, frame), "rng");   // == `frame` advances after the warm-up
+        if (s.frame) {
+            rto_check(rto_frame_launch(s.frame, pose.m, s.stream), "rto_frame_launch");
+            return;
+        }
+        memcpy(cam.c2w, pose.m, sizeof cam.c2w);
+        rto_check(rto_render(s.ctx.handle, tree.device, &cam, &opt, s.stream), "launch_renderer");
+        if (job.options.denoise) rto_check(rto_denoise(s.ctx.handle, denoiser.handle(), s.stream), "denoise");
+        if (s.h_rgba8) rto_check(rto_context_read_image_rgba8(s.ctx.handle, s.h_rgba8, s.stream), "read rgba8");
+        if (s.h_img) rto_check(rto_context_read_image(s.ctx.handle, s.h_img, s.stream), "read image");
+        if (s.h_aux) rto_check(rto_context_read_aux(s.ctx.handle, s.h_aux, s.stream), "read aux");
+    };
+    // warm up on pose 0 (main_headless.cpp:469-479): frame w of the warm-up uses the rng state after w advances
+    for (int w = 0; w < job.warmup; ++w) issue(*slots[w % job.pipe], job.trans[0], 0, w);
+    for (auto& s : slots) rto_check(rto_synchronize(s->stream), "sync");
+
+    std::unique_ptr<WriterPool> pool;
+    if (files) pool = std::make_unique<WriterPool>(job.writers < 1 ? 1 : job.writers);
+    auto retire = [&](Slot& s) {   // the slot's frame is complete on the host: hand it to a writer
+        rto_check(rto_synchronize(s.stream), "sync");
+        if (s.pending < 0) return;
+        const size_t i = (size_t)s.pending;
+        s.pending = -1;
+        if (!files) return;
+        { std::lock_guard<std::mutex> l(s.mu); s.writing = true; }
+        Slot* sp = &s;
+        pool->submit([&job, sp, i] {
+            write_outputs(job, i, sp->h_aux, sp->h_rgba8, sp->h_img);
+            { std::lock_guard<std::mutex> l(sp->mu); sp->writing = false; }
+            sp->cv.notify_all();
+        });
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = begin; i < end; ++i) {
+        Slot& s = *slots[(i - begin) % job.pipe];
+        retire(s);
+        { std::unique_lock<std::mutex> l(s.mu); s.cv.wait(l, [&] { return !s.writing; }); }   // pinned buffers free again
+        issue(s, job.trans[i], job.warmup, (int64_t)i);
+        s.pending = (long)i;
+    }
+    for (auto& s : slots) retire(*s);
+    st.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();   // results on the host
+    for (auto& s : slots) { std::unique_lock<std::mutex> l(s->mu); s->cv.wait(l, [&] { return !s->writing; }); }
+    pool.reset();
+    st.frames = (int)(end - begin);
+    st.staged = false;
+}
+
+// one GPU: frames [begin, end) of the job
+void run_shard(const Job& job, int device, size_t begin, size_t end, ShardStats& st, bool verbose) {
     if (device >= 0) rto_check(rto_set_device(device), "cudaSetDevice");
     N3Tree tree(job.tree_path);
     if (!tree.is_data_loaded()) std::exit(1);
@@ -257,15 +452,30 @@ void run_shard(const Job& job, int device, size_t begin, size_t end, float* ms, 
         tree.ndc_focal = job.fx;
     }
     tree.sync_ndc();
+    // created unconditionally, like the reference (main_headless.cpp:455-456): an empty --ts_module throws
+    std::unique_ptr<Denoiser> denoiser = std::make_unique<Denoiser>(job.ts_module);
+    if (job.pipe > 1 || job.readback.size()) {
+        run_shard_pipelined(job, tree, *denoiser, begin, end, st);
+        if (verbose) {
+            printf("pipeline: %d frames in flight, %s\n", job.pipe, job.graph ? "one CUDA-graph launch per frame" : "separate launches");
+            printf("all:    %.10f ms per frame (wall clock, results on the host)\n", 1e3 * st.wall_s / st.frames);
+            printf("FPS:    %.10f\n", st.frames / st.wall_s);
+        }
+        return;
+    }
+    // ---- the reference's protocol: one context, one stream, Timer::record (host sync) after every frame
     Camera camera(job.width, job.height, job.fx, job.fy);
-    std::vector<float> buf;
-    if (job.out_dir.size()) buf.resize((size_t)RenderContext::CHANNELS * job.width * job.height);
+    std::vector<float> buf, img;
+    std::vector<uint8_t> u8;
+    if (job.out_dir.size()) {
+        buf.resize((size_t)RenderContext::CHANNELS * job.width * job.height);
+        u8.resize((size_t)4 * job.width * job.height);
+        if (job.write_float) img.resize((size_t)4 * job.width * job.height);
+    }
     void* stream = nullptr;   // the reference creates a blocking stream (cudaStreamDefault); the legacy stream is equivalent here
     RenderContext ctx;
     ctx.offscreen = true;
     ctx.update(job.width, job.height);
-    // created unconditionally, like the reference (main_headless.cpp:455-456): an empty --ts_module throws
-    std::unique_ptr<Denoiser> denoiser = std::make_unique<Denoiser>(job.ts_module);
     const RenderOptions& options = job.options;
 
     memcpy(camera.transform, job.trans[0].m, sizeof camera.transform);
@@ -278,6 +488,7 @@ void run_shard(const Job& job, int device, size_t begin, size_t end, float* ms, 
     // frame-sharded: the rng is a pure function of the global frame index, identical to the single-GPU sequence
     rto_check(rto_context_rng_set_frame(ctx.handle, job.warmup, (int64_t)begin), "rng");
     ctx.timer().reset(stream);
+    const auto t0 = std::chrono::steady_clock::now();
     for (size_t i = begin; i < end; ++i) {
         memcpy(camera.transform, job.trans[i].m, sizeof camera.transform);
         camera._update(false);
@@ -288,28 +499,24 @@ void run_shard(const Job& job, int device, size_t begin, size_t end, float* ms, 
         ctx.timer().record(options.denoise);
         ctx.rng.advance();
         if (!job.out_dir.size()) continue;
-        if (job.write_buffer) {   // main_headless.cpp:512-523
+        if (job.write_buffer) {
             rto_check(rto_context_read_aux(ctx.handle, buf.data(), stream), "read aux");
-            rto_check(rto_synchronize(stream), "sync");
-            std::ofstream out(job.out_dir + "/buf_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
-            out.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)(buf.size() * sizeof(float)));
-        } else {                  // main_headless.cpp:524-541
-            std::vector<uint8_t> u8((size_t)4 * job.width * job.height);   // (uint8_t)(v * 255) on the device, as the reference does on the host
+        } else {   // (uint8_t)(v * 255) on the device, as the reference does on the host
             rto_check(rto_context_read_image_rgba8(ctx.handle, u8.data(), stream), "read image");
-            rto_check(rto_synchronize(stream), "sync");
-            write_png_file(job.out_dir + "/" + job.basenames[i] + ".png", u8.data(), job.width, job.height);
         }
-        if (job.write_float) {
-            std::vector<float> img((size_t)4 * job.width * job.height);
-            rto_check(rto_context_read_image(ctx.handle, img.data(), stream), "read image");
-            rto_check(rto_synchronize(stream), "sync");
-            std::ofstream out(job.out_dir + "/img_" + job.basenames[i] + ".bin", std::ios::out | std::ios::binary);
-            out.write(reinterpret_cast<const char*>(img.data()), (std::streamsize)(img.size() * sizeof(float)));
-        }
+        if (job.write_float) rto_check(rto_context_read_image(ctx.handle, img.data(), stream), "read image");
+        rto_check(rto_synchronize(stream), "sync");
+        write_outputs(job, i, buf.data(), u8.data(), img.data());
     }
     rto_check(rto_synchronize(stream), "sync");
-    rto_check(rto_timer_report(ctx.handle, ms, frames), "timer");
-    if (verbose) ctx.timer().report();
+    st.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    rto_check(rto_timer_report(ctx.handle, st.ms, &st.frames), "timer");
+    st.staged = true;
+    if (verbose) {
+        ctx.timer().report();
+        // wall-clock FPS beside the stage-sum FPS (includes the host gaps and, with -o, the file writes)
+        printf("wall:   %.10f ms per frame (wall-clock FPS %.10f)\n", 1e3 * st.wall_s / std::max(1, st.frames), st.frames / st.wall_s);
+    }
 }
 
 }  // namespace
@@ -444,6 +651,14 @@ int main(int argc, char* argv[]) {
     job.write_buffer = args.has("write_buffer");
     job.write_float = args.has("write_float");
     job.warmup = args.i("warmup", 100);
+    job.pipe = std::max(1, args.i("pipe", 1));
+    job.graph = !args.has("no_graph");
+    job.writers = args.i("writers", 4);
+    job.readback = args.str("readback");
+    if (job.readback.size() && job.readback != "rgba8" && job.readback != "float" && job.readback != "aux") {
+        fprintf(stderr, "ERROR: --readback must be rgba8, float or aux\n");
+        return 1;
+    }
     if (job.out_dir.size()) fs::create_directories(job.out_dir);
 
     // render options (main_headless.cpp:459-467; opts.cpp:44-66)
@@ -457,6 +672,10 @@ int main(int argc, char* argv[]) {
         job.options.sigma_thresh = args.f("sigma_thresh", 1e-2f);
     }
 
+    if (args.has("dump_poses")) {   // all camera transforms after the loader + convention, raw float32 [n][12] (parity tests)
+        std::ofstream pf(args.str("dump_poses"), std::ios::binary);
+        for (const Mat43& t : trans) pf.write(reinterpret_cast<const char*>(t.m), sizeof t.m);
+    }
     if (args.has("dry_run")) {
         rtohost::npz_t z = rtohost::npz_load(tree_path);
         N3Tree::HostArrays h;
@@ -476,36 +695,54 @@ int main(int argc, char* argv[]) {
 
     int num_gpus = args.i("num_gpus", 1);
     if (num_gpus < 1) num_gpus = 1;
+    std::vector<int> devices;
+    if (args.has("gpu_list")) {   // one shard per entry; an id may repeat (two host threads driving one GPU)
+        std::stringstream ss(args.str("gpu_list"));
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (tok.size()) devices.push_back(atoi(tok.c_str()));
+        if (devices.empty()) { fprintf(stderr, "ERROR: empty --gpu_list\n"); return 1; }
+        num_gpus = (int)devices.size();
+    } else {
+        for (int g = 0; g < num_gpus; ++g) devices.push_back(num_gpus == 1 ? device_id : g);
+    }
     try {
         if (num_gpus == 1) {
-            float ms[3];
-            int n = 0;
-            run_shard(job, device_id, 0, trans.size(), ms, &n, true);
+            ShardStats st;
+            run_shard(job, devices[0], 0, trans.size(), st, true);
         } else {
-            // frame sharding: contiguous slices of the pose list, one host thread and one replica per GPU, no collective
+            // frame sharding: contiguous slices of the pose list, one host thread and one replica per shard, no collective
             std::vector<std::thread> th;
-            std::vector<std::array<float, 3>> ms(num_gpus);
-            std::vector<int> frames(num_gpus, 0);
+            std::vector<ShardStats> st(num_gpus);
             const size_t n = trans.size();
             const auto t0 = std::chrono::steady_clock::now();
             for (int g = 0; g < num_gpus; ++g) {
                 const size_t b = n * g / num_gpus, e = n * (g + 1) / num_gpus;
-                th.emplace_back([&, g, b, e]() { run_shard(job, g, b, e, ms[g].data(), &frames[g], false); });
+                th.emplace_back([&, g, b, e]() { run_shard(job, devices[g], b, e, st[g], false); });
             }
             for (auto& t : th) t.join();
             const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             float agg[3] = {0, 0, 0};
             int tot = 0;
+            double slowest = 0.0;
+            bool staged = true;
             for (int g = 0; g < num_gpus; ++g) {
-                for (int k = 0; k < 3; ++k) agg[k] += ms[g][k] * frames[g];
-                tot += frames[g];
+                for (int k = 0; k < 3; ++k) agg[k] += st[g].ms[k] * st[g].frames;
+                tot += st[g].frames;
+                slowest = std::max(slowest, st[g].wall_s);
+                staged = staged && st[g].staged;
             }
-            float all = 0.f;
-            const char* names[3] = {"render", "torch: ", "filter"};
-            for (int k = 0; k < 3; ++k) { printf("%s: %.10f ms per frame\n", k == 1 ? "torch" : names[k], agg[k] / tot); all += agg[k] / tot; }
-            printf("all:    %.10f ms per frame\n", all);
-            printf("FPS:    %.10f   (per GPU; %d GPUs, %d frames, wall %.3f s incl. load + warm-up)\n", 1000.f / all, num_gpus, tot, wall);
-            printf("aggregate FPS: %.10f\n", num_gpus * 1000.f / all);
+            if (staged) {
+                float all = 0.f;
+                const char* names[3] = {"render", "torch", "filter"};
+                for (int k = 0; k < 3; ++k) { printf("%s: %.10f ms per frame\n", names[k], agg[k] / tot); all += agg[k] / tot; }
+                printf("all:    %.10f ms per frame\n", all);
+                printf("FPS:    %.10f   (per GPU; %d shards, %d frames, wall %.3f s incl. load + warm-up)\n", 1000.f / all, num_gpus, tot, wall);
+                printf("aggregate FPS: %.10f\n", num_gpus * 1000.f / all);
+            } else {
+                printf("pipeline: %d frames in flight per shard, %s\n", job.pipe, job.graph ? "one CUDA-graph launch per frame" : "separate launches");
+                printf("all:    %.10f ms per frame (wall clock of the slowest shard, results on the host)\n", 1e3 * slowest / tot);
+            }
+            printf("aggregate wall FPS: %.10f   (%d frames / slowest shard's timed loop %.4f s)\n", tot / slowest, tot, slowest);
         }
     } catch (const std::exception& e) {
         fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", e.what());

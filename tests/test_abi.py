@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(capi):
     for s in syms:
         assert hasattr(lib, s), "librtoctree_b200.so does not export %s" % s
     assert sorted(capi.EXPORTS) == syms, "capi.EXPORTS out of sync with the header"
-    assert lib.rto_abi_version() == 1
+    assert lib.rto_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly(capi):

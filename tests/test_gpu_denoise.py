@@ -43,10 +43,11 @@ def test_net_forward_simt_matches_oracle(capi, oracle, net_weights, shape):
         assert np.abs(wm.cpu().numpy() - ow).max() < 1e-6
 
 
-@pytest.mark.parametrize("shape", [(24, 40), (67, 129), (12, 60), (13, 61), (5, 7), (200, 304)])
+@pytest.mark.parametrize("shape", [(24, 40), (67, 129), (12, 60), (13, 61), (5, 7), (200, 304), (800, 800), (1080, 1920)])
 def test_net_forward_tensor_core_matches_oracle(capi, oracle, net_weights, shape):
     """tcgen05 implicit-GEMM GuidanceNet vs the oracle: identical fp16 rounding points, only the fp32 accumulation
-    order inside the tensor core differs => at most one fp16 ulp on a small fraction of the outputs."""
+    order inside the tensor core differs => at most one fp16 ulp on a small fraction of the outputs.  Includes the two
+    BASELINE frame sizes, 800x800 (14 x 80 CTA tiles) and 1920x1080, on full frames."""
     import torch
 
     H, W = shape

@@ -25,8 +25,11 @@ def _opts(capi, spp, denoise=False, **kw):
     return o
 
 
+@pytest.mark.parametrize("marcher", [0, 1], ids=["tree_walker", "production_grid"])
 @pytest.mark.parametrize("spp", [1, 2, 3, 4, 6, 8, 16, 32])
-def test_trace_bit_exact_vs_oracle(capi, oracle, mid_tree, poses8, spp):
+def test_trace_bit_exact_vs_oracle(capi, oracle, mid_tree, poses8, spp, marcher):
+    """Every trace field + the visited-leaf sequence, bit for bit against the oracle, for BOTH marching loops: the tree
+    walker and the production brick-grid marcher (rto_trace.marcher = 1: the loop rto_render runs, record switched on)."""
     from rt_octree_b200 import synthetic as S
 
     W, H = 200, 152
@@ -36,7 +39,7 @@ def test_trace_bit_exact_vs_oracle(capi, oracle, mid_tree, poses8, spp):
         cam.transform = poses8[pi]
         ctx.rng_set_frame(pi)
         assert ctx.rng_get() == oracle.frame_rng(pi)
-        tr = GpuTrace(capi, W * H, spp, max_seq=64)
+        tr = GpuTrace(capi, W * H, spp, max_seq=64, marcher=marcher)
         capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=tr.pod)
         g = tr.host()
         aux = ctx.read_aux()
@@ -57,6 +60,7 @@ def test_trace_bit_exact_vs_oracle(capi, oracle, mid_tree, poses8, spp):
         # against CPU-generated thresholds the image differs only where a threshold moved across a leaf boundary
         assert np.mean(aux[3] != o_cpu["aux"][3]) < 2e-3
         assert g["n_loads"].sum() < 0.5 * (o["depth_sum"].sum() + o["steps"].sum())
+        assert (g["term"] != -777).all()      # production marcher: grid depth / sigma agreed with the tree at every step
 
 
 def test_rng_uniforms_exact(capi, oracle, small_tree, poses8):
@@ -304,6 +308,50 @@ def test_full_size_properties(capi, oracle):
         assert np.abs(aux[:, y] - o["aux"][:, y]).max() < 1e-5
 
 
+@pytest.fixture(scope="module")
+def bench_tree():
+    """The EXACT tree bench.py times (same keyword arguments, imported from bench.py)."""
+    import bench
+    from rt_octree_b200 import synthetic as S
+
+    return S.make_tree(**bench.TREE_KW)
+
+
+@pytest.mark.parametrize("spp,denoise", [(6, True), (1, False)], ids=["config3_spp6_denoise", "config2_spp1"])
+def test_production_marcher_full_frame_bench_workload(capi, oracle, bench_tree, spp, denoise):
+    """BASELINE configs 2 and 3 on the exact bench workload (bench.py TREE_KW, 800x800, bench poses, frame rng): the
+    PRODUCTION brick-grid marcher's traversal record (steps, termination index, src / t bits, leaf-sequence hash, depth sum,
+    hit leaves and counts) equals the oracle's on EVERY pixel of the frame, and the untraced production launch writes the
+    same buffers as the traced one."""
+    import bench
+    from rt_octree_b200 import synthetic as S
+
+    W, H = bench.W, bench.H
+    poses, fx = bench.workload_poses()
+    t, ctx, cam = _setup(capi, bench_tree, W, H, fx)
+    assert t.info.max_depth == 9 and t.info.grid_level == 6
+    for f in (0, 117):
+        cam.transform = poses[f % len(poses)]
+        ctx.rng_set_frame(f, bench.WARMUP_RNG)
+        opt = _opts(capi, spp, denoise=denoise)
+        capi.launch_renderer(t, cam, opt, ctx)                                   # what bench.py times
+        aux_prod = ctx.read_aux().copy()
+        img_prod = ctx.read_image().copy()
+        tr = GpuTrace(capi, W * H, spp, marcher=1)
+        capi.launch_renderer(t, cam, opt, ctx, trace=tr.pod)                     # same loop, record on
+        g = tr.host()
+        assert np.array_equal(ctx.read_aux(), aux_prod)
+        o = oracle.render(bench_tree, poses[f % len(poses)], W, H, fx, fx, spp, oracle.frame_rng(f, bench.WARMUP_RNG),
+                          thresh=g["thresh"], want_img=True)
+        for key in TRACE_KEYS:
+            assert np.array_equal(g[key], o[key]), "%s differs on %d rays (frame %d)" % (
+                key, int((g[key] != o[key]).reshape(W * H, -1).any(1).sum()), f)
+        assert np.array_equal(aux_prod[3], o["aux"][3]) and np.abs(aux_prod - o["aux"]).max() < 1e-5
+        if not denoise:
+            assert np.abs(img_prod - o["img"]).max() < 1e-5
+        assert g["steps"].max() > 300 and (g["term"] >= 0).mean() > 0.05
+
+
 @pytest.mark.parametrize("spp", [1, 6, 16])
 def test_grid_kernel_equals_tree_walker(capi, oracle, mid_tree, poses8, spp):
     """The production (non-trace) kernel marches over the sparse brick grid; the TRACE kernel walks the tree.  Same hits
@@ -384,12 +432,16 @@ def test_tt_shaped_depth10_1080p(capi, oracle):
     k = np.rint(aux[3] * spp)
     assert np.array_equal(np.float32(k) * np.float32(1.0 / spp), aux[3]) and np.array_equal(k.reshape(-1), g["hit_cnt"].sum(1))
     assert np.array_equal(aux[4:], aux[:4] * aux[:4]) and aux[3].max() == 1.0
-    for y in (300, 540, 541, 800):
-        b, e = y * W, (y + 1) * W
-        o = oracle.render(tree, poses[41], W, H, fx, fx, spp, oracle.frame_rng(41), pix_range=(b, e), thresh=g["thresh"][b:e])
-        for key in TRACE_KEYS:
-            assert np.array_equal(g[key][b:e], o[key]), key
-        assert np.abs(aux[:, y] - o["aux"][:, y]).max() < 1e-5
+    # the production marcher's own record, FULL FRAME against the oracle (every field, every pixel)
+    trg = GpuTrace(capi, W * H, spp, marcher=1)
+    capi.launch_renderer(t, cam, _opts(capi, spp), ctx, trace=trg.pod)
+    gg = trg.host()
+    assert np.array_equal(ctx.read_aux(), aux)
+    o = oracle.render(tree, poses[41], W, H, fx, fx, spp, oracle.frame_rng(41), thresh=gg["thresh"])
+    for key in TRACE_KEYS:
+        assert np.array_equal(gg[key], o[key]), "production marcher: %s differs" % key
+        assert np.array_equal(g[key], o[key]), "tree walker: %s differs" % key
+    assert np.array_equal(aux[3], o["aux"][3]) and np.abs(aux - o["aux"]).max() < 1e-5
 
 
 def test_4k_tile_split_bands(capi, mid_tree, poses8, net_weights):

@@ -68,7 +68,7 @@ def psnr(a, b):
 class GpuTrace:
     """Device-side trace buffers (torch used only as the allocator) + the rto_trace POD."""
 
-    def __init__(self, capi, n, spp, max_seq=0, thresh=True):
+    def __init__(self, capi, n, spp, max_seq=0, thresh=True, marcher=0):
         import torch
 
         dev = "cuda"
@@ -86,6 +86,7 @@ class GpuTrace:
         for k, v in self.t.items():
             setattr(pod, k, v.data_ptr())
         pod.max_seq = max_seq
+        pod.marcher = marcher   # 0 = tree walker, 1 = production brick-grid marcher
         self.pod = pod
 
     def host(self):

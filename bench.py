@@ -7,12 +7,22 @@
 One "step" = one frame of the hot path: ray generation + octree traversal + SH shade + aux write (1 kernel) and the
 GuidanceNet + kernel-filter denoiser, on a synthetic lego-shaped PlenOctree (depth 9, data_dim 28) at 800x800, SPP 6,
 a different test pose every step.  Frames shard across ranks with no collective (weak scaling: K frames per rank).
+Every measurement repeats its K-frame block `reps` times so that the timed region lasts >= --min-seconds (0.5 s).
 Prints ONE JSON line (rank 0).  See DESIGN.md §6 for every field.
+
+Headline numbers of the line:
+  value                      frames/s with --pipe frames in flight (device-timed, max over ranks): whole-job throughput
+  value_reference_protocol   frames/s by the reference's own definition: 1000 / (render + net + filter ms), one
+                             stream, cudaEvents per stage, host sync per frame — compare THIS with reference_cuda.fps
+  e2e                        through the public API with host buffers: pose from host memory, RGBA8 image into pinned memory
+  configs                    the other BASELINE configs measured the same way (SPP 1 / no denoise; T&T-shaped depth-10 tree at
+                             1920x1080; the --write_buffer copy; the 4K tile split when WORLD_SIZE > 1)
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -31,27 +41,34 @@ SPP = 6
 N_POSES = 200
 WARMUP_RNG = 100          # main_headless.cpp:469-479: 100 warm-up advances precede pose 0
 TREE_KW = dict(depth=9, shell=1.0, halo=0.25, seed=0)
+# BASELINE config 4: Tanks-and-Temples-shaped tree (anisotropic, depth 10) at the tt loader's 1920x1080 (main_headless.cpp:274-275)
+TT_TREE_KW = dict(depth=10, shell=0.03, halo=0.02, seed=1, invradius3=(0.30, 0.42, 0.36), offset=(0.5, 0.52, 0.48))
+TT_W, TT_H, TT_FX = 1920, 1080, 1166.0
+TT_POSES_KW = dict(radius=3.2, elevation_deg=20.0)
 CACHE = os.environ.get("RTO_CACHE", "/tmp/rto_cache")
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def load_tree(rank=0, barrier=None):
-    """Synthetic lego-shaped tree, generated once per box and cached as .npy under /tmp."""
+def load_tree(rank=0, barrier=None, kw=None, tag="lego"):
+    """Synthetic tree, generated once per box and cached as .npy under /tmp."""
     from rt_octree_b200 import synthetic as S
 
-    tag = "lego_d%d_s%g_h%g_r%d" % (TREE_KW["depth"], TREE_KW["shell"], TREE_KW["halo"], TREE_KW["seed"])
-    fc, fd = os.path.join(CACHE, tag + "_child.npy"), os.path.join(CACHE, tag + "_data.npy")
+    kw = TREE_KW if kw is None else kw
+    name = "%s_d%d_s%g_h%g_r%d" % (tag, kw["depth"], kw["shell"], kw["halo"], kw["seed"])
+    fc, fd = os.path.join(CACHE, name + "_child.npy"), os.path.join(CACHE, name + "_data.npy")
     if rank == 0 and not (os.path.exists(fc) and os.path.exists(fd)):
         os.makedirs(CACHE, exist_ok=True)
-        t = S.make_tree(**TREE_KW)
+        t = S.make_tree(**kw)
         np.save(fc + ".tmp.npy", t["child"])
         np.save(fd + ".tmp.npy", t["data"])
         os.replace(fc + ".tmp.npy", fc)
         os.replace(fd + ".tmp.npy", fd)
     if barrier:
         barrier()
-    tree = {"data_dim": np.int64(28), "data_format": np.array("SH9"), "invradius3": np.full(3, 0.375, np.float32),
-            "offset": np.full(3, 0.5, np.float32), "child": np.load(fc, mmap_mode="r"), "data": np.load(fd, mmap_mode="r")}
+    tree = {"data_dim": np.int64(28), "data_format": np.array("SH9"),
+            "invradius3": np.asarray(kw.get("invradius3", (0.375,) * 3), np.float32),
+            "offset": np.asarray(kw.get("offset", (0.5,) * 3), np.float32),
+            "child": np.load(fc, mmap_mode="r"), "data": np.load(fd, mmap_mode="r")}
     return tree
 
 
@@ -59,6 +76,13 @@ def workload_poses():
     from rt_octree_b200 import synthetic as S
 
     return S.poses_to_c2w12(S.make_poses(N_POSES)), float(np.float32(S.blender_focal(W)))
+
+
+def base_config(world, K):
+    """The `config` object, identical for both arms (the reference arm measures THIS workload)."""
+    return {"workload": WORKLOAD, "poses": N_POSES, "frames_per_rank": K, "parallelism": "frame-sharded x%d" % world,
+            "tree": dict(TREE_KW), "width": W, "height": H, "spp": SPP, "denoise": True,
+            "l2": "inputs larger than L2 (tree 1.1 GB of HBM planes), a different pose every step, no flush; cold-L2 variant in value_l2_flushed"}
 
 
 class ClockSampler:
@@ -80,14 +104,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_from=None, t_to=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.p.terminate()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_from is not None and not (t_from <= ts <= t_to):
+                continue
             try:
                 sm.append(float(r[1])); smax.append(float(r[2]))
             except Exception:
@@ -100,7 +129,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_frame_seconds(tree, poses, fx, weights, frames, nthreads, want_breakdown=False):
+def cpu_frame_seconds(tree, poses, fx, weights, frames, nthreads, first_frame=0):
     """The reference's CPU implementation of the path, `frames` full frames of the workload:
     traversal/SH/composite = the reference's own trace_ray host-compiled (oracle/_ref/libref_cpu.so, OpenMP) when it
     was built, else the C port (oracle/rt_oracle.c, scalar); GuidanceNet = PyTorch CPU forward (deployed graph);
@@ -116,7 +145,7 @@ def cpu_frame_seconds(tree, poses, fx, weights, frames, nthreads, want_breakdown
     net = M.DeployedGuidanceNet(weights).eval().float()   # CPU: fp32 math on the fp16 weights
     net.forward = _fp32_forward.__get__(net)
     t_render = t_net = t_filter = 0.0
-    for f in range(frames):
+    for f in range(first_frame, first_frame + frames):
         rng = O.frame_rng(f, WARMUP_RNG)
         t0 = time.perf_counter()
         if kind == "reference":
@@ -159,13 +188,16 @@ def run_reference_arm(args):
     per0, kind, _ = cpu_frame_seconds(tree, poses, fx, weights, 1, threads)
     budget = 150.0
     steps = max(1, min(args.steps, int(budget / max(per0, 1e-3))))
-    warm = min(args.warmup, 1)
+    warm = max(0, min(args.warmup, int(20.0 / max(per0, 1e-3))))
+    if warm:
+        cpu_frame_seconds(tree, poses, fx, weights, warm, threads)
     per, kind, br = cpu_frame_seconds(tree, poses, fx, weights, steps, threads)
     fps = 1.0 / per
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {"impl": "reference", "metric": "fps_800x800_spp6_denoise", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "poses": N_POSES, "tree": TREE_KW},
+            "config": base_config(world, args.steps),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                              "sample": "%d full 800x800 SPP6 frames (trace_ray host build + torch CPU GuidanceNet + filter)" % steps,
                              "breakdown_s": br},
@@ -174,18 +206,20 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
-def algorithmic_bytes(capi, tree_h, ctx, cam, opt, poses, frames):
+def algorithmic_bytes(capi, tree_h, ctx, cam, opt, poses, frames, w, h):
     """per ray sum_steps(4*d_s + 2) + 54*n_leaf + 32 (aux) [+16 image when denoise is off], with
-    d_s = child look-ups of the REFERENCE's root-restart query — exact counters from the trace kernel (untimed)."""
+    d_s = child look-ups of the REFERENCE's root-restart query — exact counters from the PRODUCTION marcher with the
+    traversal record switched on (untimed)."""
     import torch
 
-    n = W * H
+    n = w * h
     steps = torch.zeros(n, dtype=torch.int32, device="cuda")
     dsum = torch.zeros(n, dtype=torch.int32, device="cuda")
     hits = torch.zeros(n, dtype=torch.int32, device="cuda")
     loads = torch.zeros(n, dtype=torch.int32, device="cuda")
     tr = capi.TracePOD()
     tr.steps, tr.depth_sum, tr.n_hits, tr.n_loads = steps.data_ptr(), dsum.data_ptr(), hits.data_ptr(), loads.data_ptr()
+    tr.marcher = 1
     tot = {"steps": 0, "depth_sum": 0, "hits": 0, "loads": 0}
     for f in frames:
         cam.transform = poses[f % len(poses)]
@@ -235,6 +269,152 @@ def reference_cuda_fps(tree, poses, fx, weights, frames=40):
         return {"unavailable": repr(e)[:300]}
 
 
+class Rig:
+    """One workload on this rank: tree + net + a ring of (context, stream) slots, and the three measurements."""
+
+    def __init__(self, capi, torch, tree, weights, w, h, fx, spp, denoise, poses, n_slots):
+        self.capi, self.torch = capi, torch
+        self.w, self.h, self.poses = w, h, poses
+        t0 = time.perf_counter()
+        self.tree = capi.N3Tree(tree)
+        self.load_s = time.perf_counter() - t0
+        self.net = capi.Denoiser(weights) if denoise else None
+        self.cam = capi.Camera(w, h, fx, fx)
+        self.opt = capi.RenderOptions()
+        self.opt.spp, self.opt.denoise = spp, denoise
+        self.ctxs = [capi.RenderContext(w, h) for _ in range(n_slots)]
+        self.streams = [torch.cuda.Stream() for _ in range(n_slots)]
+        self.frames_cache = {}
+
+    def close(self):
+        for fr in self.frames_cache.values():
+            for f in fr["frames"]:
+                f.close()
+        self.frames_cache = {}
+        for c in self.ctxs:
+            c.close()
+        if self.net:
+            self.net.close()
+        self.tree.close()
+
+    def frame(self, slot, f):
+        c, sp = self.ctxs[slot], self.streams[slot].cuda_stream
+        self.cam.transform = self.poses[f % len(self.poses)]
+        c.rng_set_frame(f, WARMUP_RNG)
+        self.capi.launch_renderer(self.tree, self.cam, self.opt, c, stream=sp)
+        if self.net:
+            self.net.denoise(self.cam, c, stream=sp)
+
+    # ---- device-resident throughput: CUDA events around reps x K frames issued round-robin on n_pipe slots
+    def pipelined(self, my_frames, n_pipe, warm, min_s, barrier):
+        torch, K = self.torch, len(my_frames)
+
+        def block(reps):
+            e0 = torch.cuda.Event(enable_timing=True)
+            ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_pipe)]
+            torch.cuda.synchronize()
+            barrier()
+            e0.record(self.streams[0])
+            for j in range(1, n_pipe):
+                self.streams[j].wait_event(e0)
+            i = 0
+            for _ in range(reps):
+                for f in my_frames:
+                    self.frame(i % n_pipe, f)
+                    i += 1
+            for j in range(n_pipe):
+                ends[j].record(self.streams[j])
+            torch.cuda.synchronize()
+            return max(e0.elapsed_time(e) for e in ends)
+
+        for i in range(warm):
+            self.frame(i % n_pipe, my_frames[i % K])
+        est = block(1)
+        reps = max(1, min(4000, int(math.ceil(min_s * 1e3 / max(est, 1e-3)))))
+        l0 = self.capi.launch_count()
+        ms = block(reps)
+        return {"ms_total": ms, "reps": reps, "launches": self.capi.launch_count() - l0}
+
+    # ---- the reference's Timer protocol: one stream, stage events, host sync per frame (main_headless.cpp:481-506)
+    def serial_protocol(self, my_frames, min_s):
+        ctx, K = self.ctxs[0], len(my_frames)
+        ctx.timer_enable(True)
+        for f in my_frames[:3]:
+            self.frame(0, f)
+            ctx.timer_record(bool(self.net))
+        ctx.timer_reset()
+        n, t0 = 0, time.perf_counter()
+        while True:
+            for f in my_frames:
+                self.frame(0, f)
+                ctx.timer_record(bool(self.net))
+            n += K
+            wall = time.perf_counter() - t0
+            if wall >= min_s or n >= 4000 * K:
+                break
+        ms, cnt = ctx.timer_report()
+        ctx.timer_enable(False)
+        return {"render_ms": ms[0], "net_ms": ms[1], "filter_ms": ms[2], "frames": cnt, "wall_fps": n / wall}
+
+    # ---- end to end through the public API with host buffers: the pose comes from host memory, the result lands in pinned
+    #      host memory every frame.  Ring of n_slots (context, stream, pinned buffer): the host blocks on the oldest slot only.
+    def e2e(self, my_frames, n_slots, readback, warm, min_s, barrier, graph=True):
+        capi, torch, K = self.capi, self.torch, len(my_frames)
+        shape, dt = {"rgba8": ((self.h, self.w, 4), np.uint8), "float": ((self.h, self.w, 4), np.float32),
+                     "aux": ((8, self.h, self.w), np.float32)}[readback]
+        key = (readback, n_slots, graph)
+        if key not in self.frames_cache:
+            bufs = [capi.PinnedBuffer(shape, dt) for _ in range(n_slots)]
+            frames = []
+            if graph:
+                for k in range(n_slots):
+                    frames.append(capi.Frame(self.ctxs[k], self.tree, self.net, self.opt, self.cam.fx, self.cam.fy,
+                                             **{{"rgba8": "rgba8", "float": "image", "aux": "aux"}[readback]: bufs[k]}))
+            self.frames_cache[key] = {"bufs": bufs, "frames": frames}
+        bufs, frames = self.frames_cache[key]["bufs"], self.frames_cache[key]["frames"]
+        host_poses = np.ascontiguousarray(self.poses)            # pageable host memory, read per step
+
+        def one(i, f):
+            k = i % n_slots
+            c, st = self.ctxs[k], self.streams[k]
+            st.synchronize()                                     # slot k is free again (its previous copy has landed)
+            c.rng_set_frame(f, WARMUP_RNG)
+            if graph:
+                frames[k].launch(host_poses[f % len(host_poses)], stream=st.cuda_stream)
+                return
+            self.cam.transform = host_poses[f % len(host_poses)]
+            capi.launch_renderer(self.tree, self.cam, self.opt, c, stream=st.cuda_stream)
+            if self.net:
+                self.net.denoise(self.cam, c, stream=st.cuda_stream)
+            if readback == "rgba8":
+                c.read_image_rgba8(bufs[k].array, stream=st.cuda_stream, sync=False)
+            elif readback == "float":
+                c.read_image(bufs[k].array, stream=st.cuda_stream, sync=False)
+            else:
+                c.read_aux(bufs[k].array, stream=st.cuda_stream, sync=False)
+
+        def block(reps):
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            i = 0
+            for _ in range(reps):
+                for f in my_frames:
+                    one(i, f)
+                    i += 1
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, i
+
+        for i in range(max(warm, n_slots)):
+            one(i, my_frames[i % K])
+        est, _ = block(1)
+        reps = max(1, min(4000, int(math.ceil(min_s / max(est, 1e-6)))))
+        sec, n = block(reps)
+        last = bufs[(n - 1) % n_slots].array
+        chk = int(last.sum(dtype=np.int64)) if readback == "rgba8" else float(last.sum(dtype=np.float64))
+        return {"seconds": sec, "frames": n, "reps": reps, "checksum": chk, "bytes": int(np.prod(shape)) * np.dtype(dt).itemsize}
+
+
 def run_cuda_arm(args):
     import torch
     import torch.distributed as dist
@@ -255,196 +435,185 @@ def run_cuda_arm(args):
         if world > 1:
             dist.barrier()
 
+    def reduce_max(vals):
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
     tree = load_tree(rank, barrier)
     poses, fx = workload_poses()
     weights = S.make_guidance_weights(0)
-    t0 = time.perf_counter()
-    tree_h = capi.N3Tree(tree)
-    load_s = time.perf_counter() - t0
-    info = tree_h.info
-    net = capi.Denoiser(weights)
-    cam = capi.Camera(W, H, fx, fx)
-    opt = capi.RenderOptions()
-    opt.spp, opt.denoise = SPP, True
     K, Wm = args.steps, max(args.warmup, 3)
+    min_s = args.min_seconds
     # frame sharding: rank r renders global frames r*K .. r*K+K-1 (weak scaling); rng is a pure function of the frame
     my_frames = [rank * K + i for i in range(K)]
-    NBUF = max(3, args.pipe)   # frame slots of the fp32 read-back loop (the device-timed loop uses the first --pipe)
-    NBUF8 = NBUF + 4           # frame slots of the RGBA8 read-back loop: the host blocks on the oldest slot every frame, so
-                               # a deeper ring keeps four frames queued on the GPU (measured 4/6/8 slots: 4948/5344/5374)
-    ctxs = [capi.RenderContext(W, H) for _ in range(NBUF8)]
-    streams = [torch.cuda.Stream() for _ in range(NBUF8)]
-    ctx = ctxs[0]
-    s0 = streams[0].cuda_stream
-
-    def frame(c, f, stream_ptr):
-        cam.transform = poses[f % len(poses)]
-        c.rng_set_frame(f, WARMUP_RNG)
-        capi.launch_renderer(tree_h, cam, opt, c, stream=stream_ptr)
-        net.denoise(cam, c, stream=stream_ptr)
-
-    # ---- device-resident throughput: K frames, CUDA events, max over ranks.  Frames are independent, so they are
-    #      issued alternately on two (context, stream) pairs: the long tail of one frame's render kernel (a few heavy
-    #      warps) overlaps the next frame's start.  --serial uses one stream (the reference's protocol).
     n_pipe = 1 if args.serial else args.pipe
+    NSLOT = max(args.pipe, 4) + 4   # ring of the read-back loops: the host blocks on the oldest slot every frame, so a deeper
+                                    # ring keeps four frames queued on the GPU (measured 4/6/8 slots: 4948/5344/5374 frames/s)
+    rig = Rig(capi, torch, tree, weights, W, H, fx, SPP, True, poses, NSLOT)
+    info = rig.tree.info
+
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()     # before the warm-up so that nvidia-smi is already streaming when the timed region starts
-    for i in range(Wm):
-        frame(ctxs[i % n_pipe], my_frames[i % K], streams[i % n_pipe].cuda_stream)
-    torch.cuda.synchronize()
+        clocks.start()
+    t_clk0 = clocks.mark()
+    pl = rig.pipelined(my_frames, n_pipe, Wm, min_s, barrier)
+    t_clk1 = clocks.mark()
     barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_pipe)]
-    launches0 = capi.launch_count()
-    torch.cuda.synchronize()
-    e0.record(streams[0])
-    for j in range(1, n_pipe):
-        streams[j].wait_event(e0)
-    for i, f in enumerate(my_frames):
-        frame(ctxs[i % n_pipe], f, streams[i % n_pipe].cuda_stream)
-    for j in range(n_pipe):
-        ends[j].record(streams[j])
-    torch.cuda.synchronize()
-    launches = capi.launch_count() - launches0
-    ms_total = max(e0.elapsed_time(e) for e in ends)
-    barrier()
-
-    # ---- per-kernel stage times (Timer: cudaEvents around each launch), same frames
-    ctx.timer_enable(True)
-    ctx.timer_reset()
-    for f in my_frames[: min(K, 100)]:
-        frame(ctx, f, s0)
-        ctx.timer_record(True)
-    stage_ms, _ = ctx.timer_report()
-    ctx.timer_enable(False)
+    sp = rig.serial_protocol(my_frames, min_s)
 
     # ---- cold-L2 variant: flush L2 (256 MB write) before every frame, per-frame events
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cold = []
-    with torch.cuda.stream(streams[0]):
+    with torch.cuda.stream(rig.streams[0]):
         for f in my_frames[: min(K, 30)]:
             flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            frame(ctx, f, s0)
+            rig.frame(0, f)
             b.record()
             cold.append((a, b))
     torch.cuda.synchronize()
     cold_ms = float(np.mean([a.elapsed_time(b) for a, b in cold]))
     del flush
 
-    # ---- end to end through the public API with host buffers: pose from host memory, final image read back into
-    #      pinned host memory every frame; a ring of contexts/streams so frame f's D2H overlaps the next frames' kernels.
-    #      Two read-backs of the same frames: the float4 image (what the reference CLI copies, 10.24 MB: PCIe-bound,
-    #      reported as e2e_f32) and RGBA8 converted on the device (what `volrend_headless -o` copies for the PNG, 2.56 MB:
-    #      the headline e2e).
-    pinned = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(NBUF)]
-    host_poses = np.ascontiguousarray(poses)            # pageable host memory, read per step
+    e8 = rig.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
+    ef = rig.e2e(my_frames, max(args.pipe, 3), "float", Wm, min_s, barrier, graph=not args.no_graph)
+    clk = clocks.stop(t_clk0, t_clk1) if rank == 0 else None
 
-    def e2e_frame(i, f):
-        c, st = ctxs[i % NBUF], streams[i % NBUF]
-        st.synchronize()                                 # buffer i&1 is free again (its previous D2H finished)
-        cam.transform = host_poses[f % len(poses)]
-        c.rng_set_frame(f, WARMUP_RNG)
-        capi.launch_renderer(tree_h, cam, opt, c, stream=st.cuda_stream)
-        net.denoise(cam, c, stream=st.cuda_stream)
-        c.read_image(pinned[i % NBUF].numpy(), stream=st.cuda_stream, sync=False)
+    ms_per_frame, e2e8_ms, e2ef_ms, cold_ms, render_ms, net_ms, filter_ms = reduce_max(
+        [pl["ms_total"] / (pl["reps"] * K), 1e3 * e8["seconds"] / e8["frames"], 1e3 * ef["seconds"] / ef["frames"], cold_ms,
+         sp["render_ms"], sp["net_ms"], sp["filter_ms"]])
 
-    for i in range(Wm):
-        e2e_frame(i, my_frames[i % K])
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for i, f in enumerate(my_frames):
-        e2e_frame(i, f)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    # same loop with the RGBA8 read-back (the bytes the CLI writes to PNG; a quarter of the D2H traffic)
-    pinned8 = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(NBUF8)]
-
-    def e2e8_frame(i, f):
-        c, st = ctxs[i % NBUF8], streams[i % NBUF8]
-        st.synchronize()
-        cam.transform = host_poses[f % len(poses)]
-        c.rng_set_frame(f, WARMUP_RNG)
-        capi.launch_renderer(tree_h, cam, opt, c, stream=st.cuda_stream)
-        net.denoise(cam, c, stream=st.cuda_stream)
-        c.read_image_rgba8(pinned8[i % NBUF8].numpy(), stream=st.cuda_stream, sync=False)
-
-    for i in range(max(Wm, NBUF8)):
-        e2e8_frame(i, my_frames[i % K])
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for i, f in enumerate(my_frames):
-        e2e8_frame(i, f)
-    torch.cuda.synchronize()
-    e2e8_s = time.perf_counter() - t0
-    # clocks / throttle reasons were sampled (nvidia-smi, 100 ms period) from the start of the device-timed loop to here:
-    # the timed region itself can be shorter than one sampling period, the loops after it keep the GPU under the same load
-    clk = clocks.stop() if rank == 0 else None
-    checksum = float(pinned[(K - 1) % NBUF].sum())
-    checksum8 = int(pinned8[(K - 1) % NBUF8].sum(dtype=torch.int64))
-
-    # ---- reduce over ranks: max time
-    tt = torch.tensor([ms_total, e2e_s * 1e3, cold_ms, stage_ms[0], stage_ms[1] + stage_ms[2], e2e8_s * 1e3], device="cuda",
-                      dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, cold_ms, render_ms, denoise_ms, e2e8_ms = [float(v) for v in tt.cpu()]
+    extras = {}
+    if world == 1 and not args.no_extras:
+        # ---- the --write_buffer path of config 3: the 20.48 MB guidance buffer copied to the host every frame
+        ea = rig.e2e(my_frames, max(args.pipe, 3), "aux", Wm, min_s, barrier, graph=not args.no_graph)
+        extras["e2e_aux_write_buffer"] = {
+            "value": ea["frames"] / ea["seconds"], "unit": "frames/s", "d2h_bytes_per_step": ea["bytes"], "reps": ea["reps"],
+            "checksum": ea["checksum"], "note": "same frames, aux [8][H][W] fp32 read back (main_headless.cpp:512-523): PCIe-bound"}
+    bytes_frame = counters = None
     if rank == 0:
-        bytes_frame, counters = algorithmic_bytes(capi, tree_h, ctx, cam, opt, poses, my_frames[: min(K, 8)])
+        bytes_frame, counters = algorithmic_bytes(capi, rig.tree, rig.ctxs[0], rig.cam, rig.opt, poses, my_frames[: min(K, 8)], W, H)
+
+    if world == 1 and not args.no_extras:
+        # ---- BASELINE config 2: same octree, SPP 1, denoiser off (the image comes straight out of the render kernel)
+        rig2 = Rig(capi, torch, tree, weights, W, H, fx, 1, False, poses, NSLOT)
+        p2 = rig2.pipelined(my_frames, n_pipe, Wm, min_s, barrier)
+        s2 = rig2.serial_protocol(my_frames, min_s)
+        x2 = rig2.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
+        b2, c2 = algorithmic_bytes(capi, rig2.tree, rig2.ctxs[0], rig2.cam, rig2.opt, poses, my_frames[: min(K, 8)], W, H)
+        extras["config2_spp1_no_denoise"] = {
+            "workload": "lego-synthetic depth9 800x800 spp1, denoiser off", "value": 1e3 * p2["reps"] * K / p2["ms_total"],
+            "unit": "frames/s", "streams": n_pipe, "reps": p2["reps"], "value_reference_protocol": 1e3 / s2["render_ms"],
+            "render_ms": s2["render_ms"], "serial_wall_fps": s2["wall_fps"], "e2e": x2["frames"] / x2["seconds"],
+            "e2e_d2h_bytes_per_step": x2["bytes"], "algorithmic_bytes_per_launch": b2, "per_frame": c2,
+            "roofline_achieved_gbs": b2 / (s2["render_ms"] * 1e-3) / 1e9}
+        rig2.close()
+        del rig2
+    rig_tt = None
+    if world == 1 and not args.no_extras and not args.no_tt:
+        # ---- BASELINE config 4: Tanks-and-Temples-shaped depth-10 tree at 1920x1080, SPP 6 + denoise (one GPU's share of
+        #      the frame-sharded job; frame sharding adds no per-frame work)
+        tt_tree = load_tree(rank, None, TT_TREE_KW, "tt")
+        tt_poses = S.poses_to_c2w12(S.make_poses(N_POSES, **TT_POSES_KW))
+        Ktt = min(K, 50)
+        ttf = my_frames[:Ktt]
+        rig_tt = Rig(capi, torch, tt_tree, weights, TT_W, TT_H, TT_FX, SPP, True, tt_poses, max(args.pipe, 4))
+        p4 = rig_tt.pipelined(ttf, n_pipe, Wm, min_s, barrier)
+        s4 = rig_tt.serial_protocol(ttf, min_s)
+        x4 = rig_tt.e2e(ttf, max(args.pipe, 4), "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
+        b4, c4 = algorithmic_bytes(capi, rig_tt.tree, rig_tt.ctxs[0], rig_tt.cam, rig_tt.opt, tt_poses, ttf[: min(Ktt, 4)], TT_W, TT_H)
+        i4 = rig_tt.tree.info
+        extras["config4_tt_1080p"] = {
+            "workload": "T&T-shaped synthetic depth10 (anisotropic) 1920x1080 spp6 denoise", "tree": dict(TT_TREE_KW, nodes=int(i4.capacity), leaves=int(i4.n_leaves)),
+            "value": 1e3 * p4["reps"] * Ktt / p4["ms_total"], "unit": "frames/s", "streams": n_pipe, "reps": p4["reps"], "frames_per_rep": Ktt,
+            "value_reference_protocol": 1e3 / (s4["render_ms"] + s4["net_ms"] + s4["filter_ms"]),
+            "stage_ms": {"render": s4["render_ms"], "net": s4["net_ms"], "filter": s4["filter_ms"]}, "serial_wall_fps": s4["wall_fps"],
+            "e2e": x4["frames"] / x4["seconds"], "e2e_d2h_bytes_per_step": x4["bytes"], "msamples_per_s": 1e3 * p4["reps"] * Ktt / p4["ms_total"] * TT_W * TT_H * SPP / 1e6,
+            "algorithmic_bytes_per_launch": b4, "per_frame": c4, "roofline_achieved_gbs": b4 / (s4["render_ms"] * 1e-3) / 1e9}
+        rig_tt.close()
+        del rig_tt
+    if world > 1 and not args.no_extras:
+        # ---- BASELINE config 5: single-frame latency, 3840x2160 SPP 6 + denoise split into row bands over the ranks, every
+        #      rank's filter epilogue storing its band straight into rank 0's image over NVLink (rt_octree_b200/sharding.py)
+        try:
+            from rt_octree_b200 import sharding as SH
+
+            extras["config5_4k_tile_split"] = SH.bench_tile_split(capi, torch, dist, tree, weights, poses, rank, world, local,
+                                                                   frames=30, warmup_rng=WARMUP_RNG)
+        except Exception as e:  # a side measurement must not take the headline down
+            extras["config5_4k_tile_split"] = {"unavailable": repr(e)[:300]}
+
+    if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None   # DRAM bytes per launch of the render kernel from the committed ncu --set full capture
+        traffic = traffic_src = None   # DRAM bytes per launch of the render kernel: from the committed ncu --set full capture
         try:
-            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))["dram_bytes_per_launch"])
+            tj = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))
+            traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source", "profiles/render_traffic.json")
         except Exception:
             pass
         achieved = bytes_frame / (render_ms * 1e-3) / 1e9
-        fps = world * K / (ms_total * 1e-3)
+        fps = world * 1e3 / ms_per_frame
+        fps_protocol = world * 1e3 / (render_ms + net_ms + filter_ms)
+        cfg = base_config(world, K)
+        cfg.update({"streams": n_pipe, "tree_built": dict(nodes=int(info.capacity), leaves=int(info.n_leaves), max_depth=int(info.max_depth),
+                                                          node_bytes=int(info.node_bytes), payload_bytes=int(info.payload_bytes),
+                                                          grid_bytes=int(info.grid_bytes)),
+                    "tree_load_s": rig.load_s, "min_seconds_per_measurement": min_s})
         line = {
             "metric": "fps_800x800_spp6_denoise", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_frame, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 traversal/shade, f16 GuidanceNet", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "poses": N_POSES, "frames_per_rank": K, "parallelism": "frame-sharded x%d" % world,
-                       "streams": n_pipe,
-                       "tree": dict(TREE_KW, nodes=int(info.capacity), leaves=int(info.n_leaves), max_depth=int(info.max_depth),
-                                    node_bytes=int(info.node_bytes), payload_bytes=int(info.payload_bytes)),
-                       "l2": "inputs larger than L2 (tree %.2f GB), a different pose every step, no flush; cold-L2 variant in value_l2_flushed"
-                             % ((info.node_bytes + info.payload_bytes) / 1e9),
-                       "tree_load_s": load_s},
+            "reps": pl["reps"], "timed_region_s": pl["ms_total"] * 1e-3,
+            "config": cfg,
+            "value_protocol": "%d frames in flight on %d (context, stream) pairs, device-timed over reps x steps frames" % (n_pipe, n_pipe),
+            "value_reference_protocol": fps_protocol,
+            "reference_protocol": {"definition": "1000 / (render + net + filter ms): one stream, cudaEvents per stage, host sync per frame "
+                                                 "(Timer::report, render_context.hpp:190-206)", "frames": sp["frames"],
+                                   "stage_ms": {"render": render_ms, "net": net_ms, "filter": filter_ms},
+                                   "wall_fps_incl_host_gaps": world * sp["wall_fps"]},
             "msamples_per_s": fps * W * H * SPP / 1e6,
             "value_l2_flushed": world * 1e3 / cold_ms,
-            "stage_ms": {"render": render_ms, "denoise": denoise_ms},
-            "e2e": {"value": world * K / (e2e8_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 48 + 28,
-                    "d2h_bytes_per_step": W * H * 4, "checksum": checksum8, "frame_slots": NBUF8,
-                    "readback": "RGBA8 converted on the device (rto_context_read_image_rgba8), the bytes volrend_headless -o "
+            "stage_ms": {"render": render_ms, "denoise": net_ms + filter_ms},
+            "e2e": {"value": world * 1e3 / e2e8_ms, "unit": "frames/s", "h2d_bytes_per_step": 48 + 28,
+                    "d2h_bytes_per_step": W * H * 4, "checksum": e8["checksum"], "frame_slots": NSLOT, "reps": e8["reps"],
+                    "timed_region_s": e8["seconds"], "one_graph_launch_per_frame": not args.no_graph,
+                    "readback": "RGBA8 written by the filter epilogue (rto_frame / rto_context_read_image_rgba8), the bytes volrend_headless -o "
                                 "writes to the PNG; the reference converts the same values on the host (main_headless.cpp:524-541)"},
-            "e2e_f32": {"value": world * K / (e2e_ms * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": W * H * 16,
-                        "checksum": checksum, "frame_slots": NBUF,
+            "e2e_f32": {"value": world * 1e3 / e2ef_ms, "unit": "frames/s", "d2h_bytes_per_step": W * H * 16,
+                        "checksum": ef["checksum"], "reps": ef["reps"],
                         "note": "same loop, float4 image read back (rto_context_read_image, the reference CLI's 10.24 MB copy): "
                                 "bound by the PCIe link"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(pl["launches"]),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "render_kernel<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"bound": "hbm", "kernel": "render_kernel<6,0,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": bytes_frame, "per_frame": counters,
-                         "note": "algorithmic bytes = reference-equivalent traffic (4*depth+2 per step, 54 per collided leaf, 32 aux per ray)"},
+                         "kernel_ms": render_ms,
+                         "note": "algorithmic bytes = reference-equivalent traffic (4*depth+2 per step, 54 per collided leaf, 32 aux per ray); "
+                                 "the kernel is latency/issue-bound, its physical DRAM traffic is `traffic` (see profiles/ and DESIGN.md §4.1)"},
+            "configs": extras,
         }
         if world == 1 and not args.no_baselines:
             threads = os.cpu_count() or 1
             per, kind, br = cpu_frame_seconds(tree, poses, fx, weights, args.cpu_frames, threads)
             line["cpu_baseline"] = {"value": 1.0 / per, "unit": "frames/s", "cores": threads, "kind": kind,
                                     "sample": "%d full 800x800 SPP6 frames" % args.cpu_frames, "breakdown_s": br}
-            line["reference_cuda"] = reference_cuda_fps(tree, poses, fx, weights)
+            rc = reference_cuda_fps(tree, poses, fx, weights)
+            if "fps" in rc:
+                rc["speedup_same_protocol"] = fps_protocol / rc["fps"]
+                rc["speedup_pipelined_value"] = fps / rc["fps"]
+            line["reference_cuda"] = rc
         print(json.dumps(line))
+    rig.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -457,8 +626,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames timed for the cpu_baseline sample")
     ap.add_argument("--pipe", type=int, default=4, help="frames in flight (contexts/streams) of the device-timed loop")
-    ap.add_argument("--serial", action="store_true", help="one stream, frames strictly back to back (reference protocol)")
+    ap.add_argument("--serial", action="store_true", help="one stream, frames strictly back to back, for `value` too")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="minimum duration of every timed region (the K-frame block is repeated)")
+    ap.add_argument("--no-graph", action="store_true", help="e2e loops issue separate launches instead of one rto_frame graph launch")
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / reference_cuda side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (SPP 1, T&T 1080p, write_buffer, tile split)")
+    ap.add_argument("--no-tt", action="store_true", help="skip BASELINE config 4 (saves the depth-10 tree generation)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -219,6 +219,26 @@ int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, c
                         const float* rgb_filtered_dev, const float* max_map_dev, const float* inv_kernel_sum_dev, int levels,
                         int width, int height, float* grad_weight_dev, float* grad_guidance_dev, void* stream);
 
+/* ---- single-frame tile split over several GPUs (no counterpart in the reference, which is single-GPU) ----
+ * Each GPU renders a row band (+ halo: rto_render_rect) and denoises it (rto_denoise_rows); instead of gathering the bands
+ * afterwards, the kernels that PRODUCE the final image — the filter epilogue, or the render kernel when the denoiser is off —
+ * store their rows straight into one destination image, which may live in another GPU's memory: peer-direct stores over
+ * NVLink / NVSwitch, fused with the last kernel of the frame.  `image_dev` ([H][W][4] fp32) and the optional `rgba8_dev`
+ * ([H][W][4] u8) are full-frame device pointers: another context's rto_context_image / rto_context_image_rgba8 in the same
+ * process (after rto_peer_enable), or a pointer obtained with rto_ipc_open in another process.  NULL restores the
+ * context's own buffers.  The caller orders the bands' completion before reading the destination (events / barrier), then
+ * calls rto_context_mark_image_written on the destination context so that its RGBA8 copy is known to be current. */
+int rto_context_set_image_target(rto_context* ctx, float* image_dev, unsigned char* rgba8_dev);
+int rto_context_mark_image_written(rto_context* ctx, int rgba8_too);
+int rto_peer_enable(int peer_device);                                  /* cudaDeviceEnablePeerAccess from the current device */
+int rto_ipc_export(const void* dev_ptr, unsigned char handle[64]);    /* cudaIpcGetMemHandle (dev_ptr: base of an allocation) */
+int rto_ipc_open(const unsigned char handle[64], void** dev_ptr);     /* cudaIpcOpenMemHandle, peer access enabled lazily */
+int rto_ipc_close(void* dev_ptr);
+int rto_event_create(void** event);                                    /* cross-stream / cross-device ordering without host syncs */
+int rto_event_record(void* event, void* stream);
+int rto_stream_wait_event(void* stream, void* event);
+int rto_event_destroy(void* event);
+
 /* ---- pipelined callers (no counterpart in the reference, whose driver owns one blocking stream, main_headless.cpp:445) ----
  * Non-blocking streams and pinned host memory without linking the CUDA runtime into the host program. */
 int rto_stream_create(void** stream);

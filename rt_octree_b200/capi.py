@@ -65,6 +65,8 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
     "rto_context_image_rgba8", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
     "rto_frame_create", "rto_frame_launch", "rto_frame_destroy",
+    "rto_context_set_image_target", "rto_context_mark_image_written", "rto_peer_enable", "rto_ipc_export", "rto_ipc_open",
+    "rto_ipc_close", "rto_event_create", "rto_event_record", "rto_stream_wait_event", "rto_event_destroy",
 ]
 
 _lib = None
@@ -133,6 +135,16 @@ def load(path: str = LIB_PATH):
     L.rto_frame_launch.argtypes = [P, C.POINTER(C.c_float * 12), P]
     L.rto_frame_destroy.argtypes = [P]
     L.rto_frame_destroy.restype = None
+    L.rto_context_set_image_target.argtypes = [P, P, P]
+    L.rto_context_mark_image_written.argtypes = [P, I]
+    L.rto_peer_enable.argtypes = [I]
+    L.rto_ipc_export.argtypes = [P, P]
+    L.rto_ipc_open.argtypes = [P, C.POINTER(P)]
+    L.rto_ipc_close.argtypes = [P]
+    L.rto_event_create.argtypes = [C.POINTER(P)]
+    L.rto_event_record.argtypes = [P, P]
+    L.rto_stream_wait_event.argtypes = [P, P]
+    L.rto_event_destroy.argtypes = [P]
     L.rto_timer_enable.argtypes = [P, I]
     L.rto_timer_reset.argtypes = [P]
     L.rto_timer_record.argtypes = [P, I]
@@ -260,8 +272,17 @@ class N3Tree:
             self.scale = np.full(3, np.float32(np.asarray(z["invradius"]).reshape(-1)[0]), np.float32)
         self.offset = np.asarray(z["offset"], np.float32).reshape(3).copy()
         child = np.ascontiguousarray(z["child"], np.int32)
+        if child.ndim != 4 or child.shape[0] < 1 or child.shape[2:] != (child.shape[1],) * 2:
+            raise ValueError("malformed tree.npz: child must be int32 [cap,N,N,N]")
         self.N = int(child.shape[1])
         self.capacity = int(child.shape[0])
+        cell = (self.capacity, self.N, self.N, self.N)
+
+        def expect(name, arr, shape):
+            # sizes are derived from `child`; the C ABI receives raw pointers and cannot check the lengths behind them
+            if tuple(arr.shape) != tuple(shape):
+                raise ValueError("malformed tree.npz: '%s' has shape %s, expected %s" % (name, tuple(arr.shape), tuple(shape)))
+
         L = load()
         off, sc = self.offset.ctypes.data, self.scale.ctypes.data
         if "quant_colors" in z:
@@ -275,6 +296,11 @@ class N3Tree:
             qc = np.ascontiguousarray(qc)
             sigma = np.ascontiguousarray(z["sigma"], np.float16)
             ret = np.ascontiguousarray(z["data_retained"], np.float16) if "data_retained" in z else None
+            expect("quant_colors", qc, (qm.shape[0], 65536, 3))
+            expect("quant_map", qm, (qm.shape[0],) + cell)
+            expect("sigma", sigma, cell)
+            if ret is not None:
+                expect("data_retained", ret, (ret.shape[0],) + cell + (3,))
             _check(L.rto_tree_create_quantized(C.byref(self._h), child.ctypes.data, self.capacity, self.N, self.data_dim,
                                                self.format, self.basis_dim, off, sc, qc.ctypes.data, qm.ctypes.data,
                                                int(qm.shape[0]), sigma.ctypes.data,
@@ -285,6 +311,7 @@ class N3Tree:
             if data.dtype != np.float16:
                 raise ValueError("data must be stored in half precision")
             data = np.ascontiguousarray(data)
+            expect("data", data, cell + (self.data_dim,))
             _check(L.rto_tree_create(C.byref(self._h), child.ctypes.data, data.ctypes.data, self.capacity, self.N,
                                      self.data_dim, self.format, self.basis_dim, off, sc))
 
@@ -418,6 +445,18 @@ class RenderContext:
             _cuda_sync()
         return host
 
+    @property
+    def image_rgba8_ptr(self) -> int:
+        return load().rto_context_image_rgba8(self._h)
+
+    def set_image_target(self, image_ptr=None, rgba8_ptr=None):
+        """Tile split: the kernels that produce the final image store it at these full-frame DEVICE pointers (possibly in a
+        peer GPU's memory) instead of this context's own buffers; None restores them."""
+        _check(load().rto_context_set_image_target(self._h, C.c_void_p(image_ptr), C.c_void_p(rgba8_ptr)))
+
+    def mark_image_written(self, rgba8_too=True):
+        _check(load().rto_context_mark_image_written(self._h, int(bool(rgba8_too))))
+
     def timer_enable(self, on=True):
         _check(load().rto_timer_enable(self._h, int(on)))
 
@@ -538,6 +577,27 @@ class PinnedBuffer:
             self.close()
         except Exception:
             pass
+
+
+def peer_enable(peer_device: int):
+    _check(load().rto_peer_enable(int(peer_device)))
+
+
+def ipc_export(dev_ptr: int) -> bytes:
+    h = (C.c_ubyte * 64)()
+    _check(load().rto_ipc_export(C.c_void_p(dev_ptr), h))
+    return bytes(h)
+
+
+def ipc_open(handle: bytes) -> int:
+    h = (C.c_ubyte * 64)(*handle)
+    p = C.c_void_p()
+    _check(load().rto_ipc_open(h, C.byref(p)))
+    return p.value
+
+
+def ipc_close(dev_ptr: int):
+    _check(load().rto_ipc_close(C.c_void_p(dev_ptr)))
 
 
 def stream_create() -> int:

@@ -41,6 +41,12 @@ struct rto_context {
     uchar4* img8 = nullptr;         // RGBA8 copy of img, allocated on first use; once it exists the kernels that produce img
                                     // (render with denoise off, separable filter) write it in the same epilogue
     uint64_t img_gen = 0, img8_gen = 0;   // host-side generation of img / of the RGBA8 copy (equal: img8 is current)
+    // tile split: where the kernels that produce the final image store it instead of img / img8 (rto_context_set_image_target):
+    // typically the image of ANOTHER context, possibly in a peer GPU's memory (peer-direct stores over NVLink)
+    float4* img_target = nullptr;
+    uchar4* img8_target = nullptr;
+    float4* out_img() const { return img_target ? img_target : img; }
+    uchar4* out_img8() const { return img_target ? img8_target : img8; }
     float* weight_map = nullptr;    // [6][H][W] scratch for the two-kernel denoise path
     float* guidance_map = nullptr;
     int* tile_counter = nullptr;    // [2] work counter of the persistent render kernel
@@ -422,8 +428,8 @@ static int fill_render_args(rto_context* c, const rto_tree* t, const rto_camera*
     a.adv_cols = c->adv + c->H;
     // with the denoiser on, the final image comes from rto_denoise; the reference then renders into a separate
     // noisy surface whose rgb equals aux channels 0..2 (volrend.cu:188-192 vs :205-212), so nothing is lost here
-    a.img = opt->denoise ? nullptr : c->img;
-    a.img8 = opt->denoise ? nullptr : c->img8;   // RGBA8 copy in the same store once a caller has asked for it
+    a.img = opt->denoise ? nullptr : c->out_img();
+    a.img8 = opt->denoise ? nullptr : c->out_img8();   // RGBA8 copy in the same store once a caller has asked for it
     if (trace) {
         a.tr = rto::TraceOut{trace->steps, trace->term, trace->src_bits, trace->t_bits, trace->leaf_hash,
                              trace->depth_sum, trace->n_hits, trace->n_loads, trace->hit_leaf, trace->hit_cnt,
@@ -448,7 +454,7 @@ static int render_impl(rto_context* c, const rto_tree* t, const rto_camera* cam,
     ++g_launches;
     if (a.img) {   // a full-frame or band render produced (part of) a new image
         ++c->img_gen;
-        if (a.img8 && x0 <= 0 && y0 <= 0 && x1 >= c->W && y1 >= c->H) c->img8_gen = c->img_gen;
+        if (a.img8 && !c->img_target && x0 <= 0 && y0 <= 0 && x1 >= c->W && y1 >= c->H) c->img8_gen = c->img_gen;
     }
     return RTO_OK;
 }
@@ -521,7 +527,7 @@ int rto_denoise_rows(rto_context* c, const rto_net* n, int y0, int y1, void* str
     cudaStream_t s = (cudaStream_t)stream;
     // GuidanceNet rows must cover the filter's halo: the filter at row y reads guidance rows y-L..y+L
     const int L = n->levels;
-    rto::DenoiseArgs dn{c->aux, c->img, c->weight_map, c->guidance_map, c->W, c->H, y0 - L < 0 ? 0 : y0 - L,
+    rto::DenoiseArgs dn{c->aux, c->out_img(), c->weight_map, c->guidance_map, c->W, c->H, y0 - L < 0 ? 0 : y0 - L,
                         y1 + L > c->H ? c->H : y1 + L};
     const bool tc = n->impl == 0 && n->tc_capable();
     timer_start(c, 1, s);
@@ -530,15 +536,15 @@ int rto_denoise_rows(rto_context* c, const rto_net* n, int y0, int y1, void* str
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch (%s): %s", tc ? "tcgen05" : "simt", cudaGetErrorString(e));
     timer_start(c, 2, s);
     if (tc)   // guidance is relu6-bounded here, so the precomputed-exp filter applies
-        e = rto::launch_filter_fast(c->aux, c->weight_map, c->guidance_map, c->W, c->H, y0, y1, c->img, c->img8, s);
+        e = rto::launch_filter_fast(c->aux, c->weight_map, c->guidance_map, c->W, c->H, y0, y1, c->out_img(), c->out_img8(), s);
     else
         e = rto::launch_filter_simt(c->aux, (size_t)c->W * c->H, 1, c->weight_map, c->guidance_map, L, c->W, c->H, y0, y1,
-                                    c->img, s);
+                                    c->out_img(), s);
     timer_stop(c, 2, s);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "filter launch: %s", cudaGetErrorString(e));
     g_launches += 2;
     ++c->img_gen;
-    if (tc && c->img8 && y0 <= 0 && y1 >= c->H) c->img8_gen = c->img_gen;   // the filter wrote the RGBA8 copy as well
+    if (tc && c->img8 && !c->img_target && y0 <= 0 && y1 >= c->H) c->img8_gen = c->img_gen;   // the filter wrote the RGBA8 copy as well
     return RTO_OK;
 }
 int rto_denoise(rto_context* c, const rto_net* n, void* stream) {
@@ -600,6 +606,71 @@ int rto_filter_backward(const float* grad_output_dev, const float* img_in_dev, c
     return RTO_OK;
 }
 
+
+// --------------------------------------------------------------------------- tile split: peer-direct image stores
+int rto_context_set_image_target(rto_context* c, float* image_dev, unsigned char* rgba8_dev) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    if (!image_dev && rgba8_dev) return fail(RTO_ERR_INVALID, "an RGBA8 target needs an image target");
+    c->img_target = reinterpret_cast<float4*>(image_dev);
+    c->img8_target = reinterpret_cast<uchar4*>(rgba8_dev);
+    return RTO_OK;
+}
+int rto_context_mark_image_written(rto_context* c, int rgba8_too) {
+    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
+    ++c->img_gen;
+    if (rgba8_too && c->img8) c->img8_gen = c->img_gen;
+    return RTO_OK;
+}
+int rto_peer_enable(int peer_device) {
+    int dev = 0;
+    RTO_CUDA(cudaGetDevice(&dev));
+    if (dev == peer_device) return RTO_OK;
+    int can = 0;
+    RTO_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return fail(RTO_ERR_UNSUPPORTED, "device %d cannot access device %d directly", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return RTO_OK; }
+    if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    return RTO_OK;
+}
+int rto_ipc_export(const void* dev_ptr, unsigned char handle[64]) {
+    if (!dev_ptr || !handle) return fail(RTO_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    RTO_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return RTO_OK;
+}
+int rto_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+    if (!dev_ptr || !handle) return fail(RTO_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    RTO_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTO_OK;
+}
+int rto_ipc_close(void* dev_ptr) {
+    if (dev_ptr) RTO_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return RTO_OK;
+}
+int rto_event_create(void** event) {
+    if (!event) return fail(RTO_ERR_INVALID, "event is NULL");
+    cudaEvent_t e = nullptr;
+    RTO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *event = (void*)e;
+    return RTO_OK;
+}
+int rto_event_record(void* event, void* stream) {
+    RTO_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return RTO_OK;
+}
+int rto_stream_wait_event(void* stream, void* event) {
+    RTO_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return RTO_OK;
+}
+int rto_event_destroy(void* event) {
+    if (event) RTO_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return RTO_OK;
+}
 
 // ------------------------------------------------------------------------------- streams, pinned memory, frame graph
 int rto_stream_create(void** stream) {

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -59,7 +60,7 @@ struct Args {
 Args parse_args(int argc, char** argv) {
     static const std::map<std::string, std::string> shorts = {{"w", "width"}, {"h", "height"}, {"s", "step_size"}, {"e", "stop_thresh"},
                                                               {"a", "sigma_thresh"}, {"o", "write_images"}, {"i", "intrin"}, {"r", "reverse_yz"}};
-    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float", "no_graph"};
+    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float", "no_graph", "tile_split"};
     Args a;
     for (int k = 1; k < argc; ++k) {
         std::string t = argv[k];
@@ -107,6 +108,8 @@ void print_help() {
          "      --write_buffer      save auxiliary buffers (buf_<name>.bin). Invalid if output directory is not given.\n"
          "      --num_gpus arg      shard the poses over this many GPUs (default: 1)\n"
          "      --gpu_list arg      comma-separated device ids, one shard per entry (e.g. 0,1,2,3; 0,0 = two shards on GPU 0)\n"
+         "      --tile_split        single-frame latency mode: every frame is cut into row bands over the GPUs of --num_gpus /\n"
+         "                          --gpu_list; each band's filter stores into GPU 0's image over NVLink (no gather)\n"
          "      --pipe arg          frames in flight per GPU: N contexts/streams, CUDA-graph frames (default: 1 = reference protocol)\n"
          "      --no_graph          with --pipe: issue the kernels separately instead of one graph launch per frame\n"
          "      --readback arg      copy rgba8 | float | aux to pinned host memory every frame even without -o\n"
@@ -281,7 +284,7 @@ struct Job {
     RenderOptions options;
     int width, height;
     float fx, fy;
-    bool llff, write_buffer, write_float, graph;
+    bool llff, write_buffer, write_float, graph, tile_split;
     int warmup, pipe, writers;
 };
 
@@ -440,6 +443,127 @@ void run_shard_pipelined(const Job& job, N3Tree& tree, Denoiser& denoiser, size_
     st.staged = false;
 }
 
+// reusable spinning barrier for the per-frame rendezvous of the tile-split threads (a frame lasts a few hundred microseconds:
+// a sleeping barrier would cost more than the work it orders)
+class SpinBarrier {
+   public:
+    explicit SpinBarrier(int n) : n_(n) {}
+    void wait() {
+        const int gen = gen_.load(std::memory_order_acquire);
+        if (count_.fetch_add(1, std::memory_order_acq_rel) == n_ - 1) {
+            count_.store(0, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
+        } else {
+            while (gen_.load(std::memory_order_acquire) == gen) {}
+        }
+    }
+   private:
+    const int n_;
+    std::atomic<int> count_{0}, gen_{0};
+};
+
+// --tile_split: single-frame latency mode.  One host thread per GPU; for every frame each thread renders the
+// rows of its band plus the denoiser's halo (2 rows for the two 3x3 convolutions + L for the largest filter level), runs the
+// GuidanceNet and the filter on its band, and the filter's epilogue stores the band directly into GPU 0's image (float4 and
+// RGBA8) through a peer mapping — no gather, no halo exchange.  GPU 0's stream waits on one event per band, then copies the
+// assembled frame to the host.  Latency = rendezvous of the threads -> frame in host memory.
+void run_tile_split(const Job& job, const std::vector<int>& devices) {
+    const int n = (int)devices.size(), W = job.width, H = job.height;
+    const size_t px = (size_t)W * H;
+    const size_t frames = job.trans.size();
+    SpinBarrier bar(n);
+    std::vector<void*> events(n, nullptr);
+    std::vector<std::string> errors(n);
+    std::atomic<bool> failed{false};
+    float* dst_img = nullptr;          // GPU 0's image / RGBA8 copy: the destination of every band
+    unsigned char* dst_img8 = nullptr;
+    int levels = 4;
+    std::vector<double> lat_ms;
+    const rto_render_options opt = job.options.pod();
+    auto worker = [&](int g) {
+        try {
+            rto_check(rto_set_device(devices[g]), "cudaSetDevice");
+            N3Tree tree(job.tree_path);
+            if (!tree.is_data_loaded()) throw std::runtime_error("tree not loaded");
+            if (job.llff) { tree.use_ndc = true; tree.ndc_width = (float)W; tree.ndc_height = (float)H; tree.ndc_focal = job.fx; }
+            tree.sync_ndc();
+            Denoiser denoiser(job.ts_module);
+            RenderContext ctx;
+            ctx.update(W, H);
+            void* stream = nullptr;
+            rto_check(rto_stream_create(&stream), "stream");
+            rto_check(rto_event_create(&events[g]), "event");
+            uint8_t* h8 = nullptr;
+            float *himg = nullptr, *haux = nullptr;
+            if (g == 0) {
+                dst_img = rto_context_image(ctx.handle);
+                dst_img8 = rto_context_image_rgba8(ctx.handle);
+                levels = denoiser.levels();
+                rto_check(rto_host_alloc(reinterpret_cast<void**>(&h8), px * 4), "pinned rgba8");
+                if (job.write_float) rto_check(rto_host_alloc(reinterpret_cast<void**>(&himg), px * 16), "pinned image");
+            }
+            bar.wait();   // destination pointers published
+            if (g != 0) {
+                rto_check(rto_peer_enable(devices[0]), "peer access to the first GPU");
+                rto_check(rto_context_set_image_target(ctx.handle, dst_img, dst_img8), "image target");
+            }
+            const int halo = job.options.denoise ? 2 + levels : 0;
+            const int b0 = (int)((int64_t)H * g / n), b1 = (int)((int64_t)H * (g + 1) / n);
+            const int r0 = std::max(0, b0 - halo), r1 = std::min(H, b1 + halo);
+            rto_camera cam{};
+            cam.width = W; cam.height = H; cam.fx = job.fx; cam.fy = job.fy;
+            auto one = [&](const Mat43& pose, int64_t warm, int64_t frame, bool timed, size_t out_index) {
+                bar.wait();
+                const auto t0 = std::chrono::steady_clock::now();
+                memcpy(cam.c2w, pose.m, sizeof cam.c2w);
+                rto_check(rto_context_rng_set_frame(ctx.handle, warm, frame), "rng");
+                rto_check(rto_render_rect(ctx.handle, tree.device, &cam, &opt, 0, r0, W, r1, stream), "render band");
+                if (job.options.denoise) rto_check(rto_denoise_rows(ctx.handle, denoiser.handle(), b0, b1, stream), "denoise band");
+                rto_check(rto_event_record(events[g], stream), "event");
+                bar.wait();   // every band's completion event has been recorded
+                if (g == 0) {
+                    for (int k = 1; k < n; ++k) rto_check(rto_stream_wait_event(stream, events[k]), "wait band");
+                    rto_check(rto_context_mark_image_written(ctx.handle, 1), "mark");
+                    rto_check(rto_context_read_image_rgba8(ctx.handle, h8, stream), "read rgba8");
+                    if (himg) rto_check(rto_context_read_image(ctx.handle, himg, stream), "read image");
+                    rto_check(rto_synchronize(stream), "sync");
+                    if (timed) lat_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                    if (timed && job.out_dir.size()) write_outputs(job, out_index, nullptr, h8, himg);
+                } else {
+                    rto_check(rto_synchronize(stream), "sync");
+                }
+            };
+            for (int w = 0; w < job.warmup; ++w) one(job.trans[0], 0, w, false, 0);
+            for (size_t i = 0; i < frames; ++i) one(job.trans[i], job.warmup, (int64_t)i, true, i);
+            bar.wait();
+            if (g != 0) rto_context_set_image_target(ctx.handle, nullptr, nullptr);
+            rto_host_free(h8); rto_host_free(himg); rto_host_free(haux);
+            rto_event_destroy(events[g]);
+            rto_stream_destroy(stream);
+        } catch (const std::exception& e) {
+            errors[g] = e.what();
+            failed = true;
+            fprintf(stderr, "tile split, GPU slot %d: %s\n", g, e.what());
+            std::exit(134);   // the other threads are parked in the barrier: leave as a whole
+        }
+    };
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; ++g) th.emplace_back(worker, g);
+    for (auto& t : th) t.join();
+    if (lat_ms.empty()) return;
+    std::vector<double> s = lat_ms;
+    std::sort(s.begin(), s.end());
+    double mean = 0;
+    for (double v : lat_ms) mean += v;
+    mean /= (double)lat_ms.size();
+    printf("tile split: %d bands over GPUs [", n);
+    for (int g = 0; g < n; ++g) printf("%s%d", g ? "," : "", devices[g]);
+    printf("], %dx%d, halo %d rows, peer-direct stores into the first GPU\n", W, H, job.options.denoise ? 2 + levels : 0);
+    printf("latency: median %.6f ms, mean %.6f ms, min %.6f ms per frame (rendezvous -> RGBA8 frame on the host, %zu frames)\n",
+           s[s.size() / 2], mean, s.front(), lat_ms.size());
+    printf("FPS:    %.10f   (1000 / median latency)\n", 1000.0 / s[s.size() / 2]);
+}
+
 // one GPU: frames [begin, end) of the job
 void run_shard(const Job& job, int device, size_t begin, size_t end, ShardStats& st, bool verbose) {
     if (device >= 0) rto_check(rto_set_device(device), "cudaSetDevice");
@@ -521,7 +645,7 @@ void run_shard(const Job& job, int device, size_t begin, size_t end, ShardStats&
 
 }  // namespace
 
-int main(int argc, char* argv[]) {
+static int run_main(int argc, char* argv[]) {
     Args args = parse_args(argc, argv);
     if (args.has("help")) { print_help(); return 0; }
     std::string tree_path = args.str("file");
@@ -655,6 +779,11 @@ int main(int argc, char* argv[]) {
     job.graph = !args.has("no_graph");
     job.writers = args.i("writers", 4);
     job.readback = args.str("readback");
+    job.tile_split = args.has("tile_split");
+    if (job.tile_split && job.write_buffer) {
+        fprintf(stderr, "ERROR: --tile_split assembles the final image only; --write_buffer needs the frame-sharded modes\n");
+        return 1;
+    }
     if (job.readback.size() && job.readback != "rgba8" && job.readback != "float" && job.readback != "aux") {
         fprintf(stderr, "ERROR: --readback must be rgba8, float or aux\n");
         return 1;
@@ -706,7 +835,9 @@ int main(int argc, char* argv[]) {
         for (int g = 0; g < num_gpus; ++g) devices.push_back(num_gpus == 1 ? device_id : g);
     }
     try {
-        if (num_gpus == 1) {
+        if (job.tile_split) {
+            run_tile_split(job, devices);
+        } else if (num_gpus == 1) {
             ShardStats st;
             run_shard(job, devices[0], 0, trans.size(), st, true);
         } else {
@@ -749,4 +880,15 @@ int main(int argc, char* argv[]) {
         return 134;
     }
     return 0;
+}
+
+// Logic errors are C++ exceptions in the reference and end the process through std::terminate (exit status 134); here they
+// are reported the same way, without the core dump.
+int main(int argc, char* argv[]) {
+    try {
+        return run_main(argc, argv);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "terminate called after throwing an instance of 'std::runtime_error'\n  what():  %s\n", e.what());
+        return 134;
+    }
 }

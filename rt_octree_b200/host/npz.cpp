@@ -3,6 +3,8 @@
 
 #include <zlib.h>
 
+#include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -62,10 +64,13 @@ NpyArray parse_npy(const unsigned char* buf, size_t len) {
     const std::string h(reinterpret_cast<const char*>(buf + hoff), hlen);
     NpyArray a;
     // 'descr': '<f2'
+    const size_t npos = std::string::npos;
     size_t p = h.find("'descr'");
-    if (p == std::string::npos) throw std::runtime_error("npy header: no descr");
-    p = h.find('\'', h.find(':', p));
-    const size_t q = h.find('\'', p + 1);
+    if (p == npos) throw std::runtime_error("npy header: no descr");
+    const size_t colon = h.find(':', p);
+    p = colon == npos ? npos : h.find('\'', colon);
+    const size_t q = p == npos ? npos : h.find('\'', p + 1);
+    if (q == npos) throw std::runtime_error("npy header: bad descr");
     const std::string descr = h.substr(p + 1, q - p - 1);
     if (descr.size() < 2) throw std::runtime_error("npy header: bad descr");
     size_t k = 0;
@@ -75,11 +80,15 @@ NpyArray parse_npy(const unsigned char* buf, size_t len) {
     const size_t width = (size_t)atoi(descr.c_str() + k + 1);
     a.word_size = a.kind == 'U' ? 4 * width : width;
     p = h.find("'fortran_order'");
-    a.fortran_order = p != std::string::npos && h.compare(h.find(':', p) + 2, 4, "True") == 0;
+    if (p != npos) {
+        const size_t c2 = h.find(':', p);
+        a.fortran_order = c2 != npos && c2 + 6 <= h.size() && h.compare(c2 + 2, 4, "True") == 0;
+    }
     p = h.find("'shape'");
-    if (p == std::string::npos) throw std::runtime_error("npy header: no shape");
+    if (p == npos) throw std::runtime_error("npy header: no shape");
     p = h.find('(', p);
-    const size_t e = h.find(')', p);
+    const size_t e = p == npos ? npos : h.find(')', p);
+    if (e == npos) throw std::runtime_error("npy header: bad shape");
     const std::string sh = h.substr(p + 1, e - p - 1);
     size_t i = 0;
     while (i < sh.size()) {
@@ -88,8 +97,13 @@ NpyArray parse_npy(const unsigned char* buf, size_t len) {
         a.shape.push_back((size_t)strtoull(sh.c_str() + i, nullptr, 10));
         while (i < sh.size() && sh[i] != ',') ++i;
     }
-    const size_t nbytes = a.num_vals() * a.word_size;
-    if (hoff + hlen + nbytes > len) throw std::runtime_error("truncated npy payload");
+    // element count and byte size with overflow checks (a crafted shape must not wrap around the bounds test below)
+    size_t nbytes = a.word_size;
+    for (size_t d : a.shape) {
+        if (d != 0 && nbytes > SIZE_MAX / d) throw std::runtime_error("npy header: shape overflows");
+        nbytes *= d;
+    }
+    if (nbytes > len || hoff + hlen > len - nbytes) throw std::runtime_error("truncated npy payload");
     a.bytes.assign(buf + hoff + hlen, buf + hoff + hlen + nbytes);
     return a;
 }
@@ -101,7 +115,10 @@ NpyArray npy_load(const std::string& path) {
 
 npz_t npz_load(const std::string& path) {
     const auto buf = read_file(path);
-    const size_t n = buf.size();
+    return npz_load_mem(buf.data(), buf.size(), path);
+}
+
+npz_t npz_load_mem(const unsigned char* buf, size_t n, const std::string& path) {
     if (n < 22) throw std::runtime_error("npz too small: " + path);
     // end-of-central-directory record (search backwards), zip64 locator if present
     size_t eocd = std::string::npos;
@@ -114,41 +131,53 @@ npz_t npz_load(const std::string& path) {
     uint64_t cd_off = rd32(&buf[eocd + 16]);
     if (eocd >= 20 && rd32(&buf[eocd - 20]) == 0x07064b50u) {  // zip64 EOCD locator
         const uint64_t z64 = rd64(&buf[eocd - 20 + 8]);
-        if (z64 + 56 <= n && rd32(&buf[z64]) == 0x06064b50u) {
+        if (z64 <= n && 56 <= n - z64 && rd32(&buf[z64]) == 0x06064b50u) {
             n_entries = rd64(&buf[z64 + 32]);
             cd_off = rd64(&buf[z64 + 48]);
         }
     }
     npz_t out;
+    if (cd_off > n) throw std::runtime_error("npz: bad central directory offset");
     size_t p = (size_t)cd_off;
     for (uint64_t e = 0; e < n_entries; ++e) {
-        if (p + 46 > n || rd32(&buf[p]) != 0x02014b50u) throw std::runtime_error("npz: bad central directory");
+        if (p > n || 46 > n - p || rd32(&buf[p]) != 0x02014b50u) throw std::runtime_error("npz: bad central directory");
         const uint16_t method = rd16(&buf[p + 10]);
         uint64_t csize = rd32(&buf[p + 20]), usize = rd32(&buf[p + 24]);
         const uint16_t nlen = rd16(&buf[p + 28]), xlen = rd16(&buf[p + 30]), clen = rd16(&buf[p + 32]);
         uint64_t lho = rd32(&buf[p + 42]);
+        // name, extra field and comment must lie inside the buffer before any of them is read
+        if ((size_t)nlen + xlen + clen > n - p - 46) throw std::runtime_error("npz: central directory entry runs past the end");
         std::string name(reinterpret_cast<const char*>(&buf[p + 46]), nlen);
-        // zip64 extra field
+        // zip64 extra field: 8-byte values, present only for the 32-bit fields that hold 0xffffffff, in this order
         size_t x = p + 46 + nlen;
         const size_t xend = x + xlen;
         while (x + 4 <= xend) {
             const uint16_t id = rd16(&buf[x]), sz = rd16(&buf[x + 2]);
+            if ((size_t)sz > xend - x - 4) throw std::runtime_error("npz: extra field runs past its record");
             if (id == 0x0001) {
                 size_t y = x + 4;
-                if (usize == 0xffffffffu) { usize = rd64(&buf[y]); y += 8; }
-                if (csize == 0xffffffffu) { csize = rd64(&buf[y]); y += 8; }
-                if (lho == 0xffffffffu) { lho = rd64(&buf[y]); y += 8; }
+                const size_t yend = x + 4 + sz;
+                auto take64 = [&](uint64_t& v) {
+                    if (8 > yend - y) throw std::runtime_error("npz: short zip64 extra field");
+                    v = rd64(&buf[y]);
+                    y += 8;
+                };
+                if (usize == 0xffffffffu) take64(usize);
+                if (csize == 0xffffffffu) take64(csize);
+                if (lho == 0xffffffffu) take64(lho);
             }
             x += 4 + sz;
         }
         p = xend + clen;
-        if (lho + 30 > n || rd32(&buf[lho]) != 0x04034b50u) throw std::runtime_error("npz: bad local header");
-        const size_t doff = (size_t)lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
-        if (doff + csize > n) throw std::runtime_error("npz: truncated member " + name);
+        if (lho > n || 30 > n - lho || rd32(&buf[lho]) != 0x04034b50u) throw std::runtime_error("npz: bad local header");
+        const uint64_t doff64 = lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
+        if (doff64 > n || csize > n - doff64) throw std::runtime_error("npz: truncated member " + name);
+        const size_t doff = (size_t)doff64;
         if (name.size() > 4 && name.substr(name.size() - 4) == ".npy") name.resize(name.size() - 4);
         if (method == 0) {
             out[name] = parse_npy(&buf[doff], (size_t)csize);
         } else if (method == 8) {
+            if (usize > ((uint64_t)1 << 40)) throw std::runtime_error("npz: implausible member size for " + name);
             std::vector<unsigned char> raw((size_t)usize);
             z_stream zs;
             memset(&zs, 0, sizeof zs);

@@ -35,5 +35,7 @@ using npz_t = std::map<std::string, NpyArray>;
 NpyArray parse_npy(const unsigned char* buf, size_t len);
 NpyArray npy_load(const std::string& path);
 npz_t npz_load(const std::string& path);
+// the same from a memory image of the file (cnpy::npz_load_mem, used by N3Tree::open_mem); `what` names it in error messages
+npz_t npz_load_mem(const unsigned char* buf, size_t len, const std::string& what = "<memory>");
 
 }  // namespace rtohost

@@ -102,6 +102,15 @@ struct N3Tree {
         }
     }
 
+    // N3Tree::open_mem (n3tree.hpp:32, src/n3tree.cpp:156-172): the same file as a memory image ("for web mostly" there)
+    void open_mem(const char* data, uint64_t size) {
+        rto_tree_destroy(device);
+        device = nullptr;
+        rtohost::npz_t npz = rtohost::npz_load_mem(reinterpret_cast<const unsigned char*>(data), (size_t)size);
+        load_npz(npz);
+        use_ndc = false;
+    }
+
     // call after changing use_ndc / ndc_* (main_headless.cpp:400-405 sets them after construction)
     void sync_ndc() const {
         if (device) rto_check(rto_tree_set_ndc(device, use_ndc ? ndc_width : -1.f, ndc_height, ndc_focal), "rto_tree_set_ndc");
@@ -159,50 +168,63 @@ struct N3Tree {
         h.N = (int)child.shape[1];
         h.child = child.data<int32_t>();
         if (h.N != 2) fprintf(stderr, "WARNING: N != 2 probably doesn't work.\n");
-        const int N = h.N, data_dim = h.data_dim;
-        const size_t n_child = child.shape[0] * (size_t)N * N * N;
+        const size_t N = (size_t)h.N, cap = child.shape[0], data_dim = (size_t)h.data_dim;
+        if (cap == 0 || cap >= ((size_t)1 << 28) || child.shape[2] != N || child.shape[3] != N || h.data_dim < 1)
+            throw std::runtime_error("malformed tree.npz: child shape / data_dim");
+        const size_t n_child = cap * N * N * N;
         h.n_child = n_child;
-        if (npz.count("quant_colors")) {   // median-cut codebook decode, src/n3tree.cpp:279-340
+        h.capacity = (int)cap;
+        // Every array is uploaded with sizes derived from `child` ([cap,N,N,N]); a file whose arrays disagree with it must be
+        // rejected HERE, because the C ABI receives raw pointers and cannot see the lengths behind them.
+        auto expect = [&](const rtohost::NpyArray& a, const char* name, std::vector<size_t> shape, size_t word) {
+            bool ok = a.word_size == word && a.shape.size() == shape.size() && !a.fortran_order;
+            for (size_t i = 0; ok && i < shape.size(); ++i) ok = a.shape[i] == shape[i];
+            if (!ok) throw std::runtime_error(std::string("malformed tree.npz: '") + name + "' has the wrong shape or type");
+        };
+        if (child.fortran_order) throw std::runtime_error("malformed tree.npz: 'child' is in Fortran order");
+        if (npz.count("quant_colors")) {   // median-cut codebook files, src/n3tree.cpp:279-340
             fprintf(stderr, "INFO: Decoding quantized colors\n");
             const rtohost::NpyArray& qc = npz["quant_colors"];
             if (qc.word_size != 2) throw std::runtime_error("codebook must be stored in half precision");
             const rtohost::NpyArray& qm = need("quant_map");
-            h.capacity = (int)qm.shape[1];
-            int n_basis = (int)qm.shape[0];
-            if ((int)qc.shape[0] != n_basis) throw std::runtime_error("codebook and map basis numbers does not match");
-            const int n_ret = npz.count("data_retained") ? (int)npz["data_retained"].shape[0] : 0;
-            const uint16_t* sig = need("sigma").data<uint16_t>();
-            const uint16_t* map = qm.data<uint16_t>();
-            const uint16_t* col = qc.data<uint16_t>();
-            const uint16_t* r = n_ret ? npz["data_retained"].data<uint16_t>() : nullptr;
+            if (qm.shape.empty() || qc.shape.empty() || qc.shape[0] != qm.shape[0])
+                throw std::runtime_error("codebook and map basis numbers does not match");
+            const size_t n_q = qm.shape[0];
+            const size_t n_ret = npz.count("data_retained") ? (npz["data_retained"].shape.empty() ? 0 : npz["data_retained"].shape[0]) : 0;
+            expect(qc, "quant_colors", {n_q, 65536, 3}, 2);
+            expect(qm, "quant_map", {n_q, cap, N, N, N}, 2);
+            expect(need("sigma"), "sigma", {cap, N, N, N}, 2);
+            if (n_ret) expect(npz["data_retained"], "data_retained", {n_ret, cap, N, N, N, 3}, 2);
+            if (n_q + n_ret == 0 || 3 * (n_q + n_ret) > data_dim - 1) throw std::runtime_error("malformed tree.npz: codebook count does not fit data_dim");
             h.quantized = true;
-            h.quant_colors = col; h.quant_map = map; h.sigma = sig; h.retained = r;
-            h.n_quant = n_basis; h.n_retained = n_ret;
+            h.quant_colors = qc.data<uint16_t>(); h.quant_map = qm.data<uint16_t>(); h.sigma = need("sigma").data<uint16_t>();
+            h.retained = n_ret ? npz["data_retained"].data<uint16_t>() : nullptr;
+            h.n_quant = (int)n_q; h.n_retained = (int)n_ret;
             if (!decode_on_host) return;
-            n_basis += n_ret;
-            h.decoded.assign(n_child * (size_t)data_dim * 2, 0);
+            // Host materialisation of the dense array (only `--dry_run` needs it; the product gathers on the GPU).  Slot layout
+            // of a leaf record (n3tree.cpp:301-338): colour channel k of basis function b sits at b + k*n_basis, retained basis
+            // functions first, then the quantised ones; sigma last.  Written basis-major so each source plane streams once.
+            const size_t n_basis = n_q + n_ret;
+            h.decoded.assign(n_child * data_dim * 2, 0);
             uint16_t* out = reinterpret_cast<uint16_t*>(h.decoded.data());
-            for (size_t i = 0; i < n_child; ++i) {
-                const size_t off = i * (size_t)data_dim;
-                for (int j = 0; j < n_basis - n_ret; ++j) {
-                    size_t boff = off + j + n_ret;
-                    const int id = map[(size_t)j * n_child + i];
-                    const uint16_t* c = col + (size_t)j * 65536 * 3 + (size_t)id * 3;
-                    for (int k = 0; k < 3; ++k) { out[boff] = c[k]; boff += n_basis; }
-                }
-                out[off + data_dim - 1] = sig[i];
+            auto colour_slot = [&](size_t leaf, size_t basis, size_t k) -> uint16_t& { return out[leaf * data_dim + basis + k * n_basis]; };
+            for (size_t b = 0; b < n_ret; ++b) {
+                const uint16_t* src = h.retained + b * n_child * 3;
+                for (size_t leaf = 0; leaf < n_child; ++leaf)
+                    for (size_t k = 0; k < 3; ++k) colour_slot(leaf, b, k) = src[leaf * 3 + k];
             }
-            for (size_t i = 0; n_ret && i < n_child; ++i)
-                for (int j = 0; j < n_ret; ++j) {
-                    size_t boff = i * (size_t)data_dim + j;
-                    const uint16_t* c = r + (size_t)j * n_child * 3 + i * 3;
-                    for (int k = 0; k < 3; ++k) { out[boff] = c[k]; boff += n_basis; }
-                }
+            for (size_t q = 0; q < n_q; ++q) {
+                const uint16_t* book = h.quant_colors + q * 65536 * 3;
+                const uint16_t* idx = h.quant_map + q * n_child;
+                for (size_t leaf = 0; leaf < n_child; ++leaf)
+                    for (size_t k = 0; k < 3; ++k) colour_slot(leaf, n_ret + q, k) = book[(size_t)idx[leaf] * 3 + k];
+            }
+            for (size_t leaf = 0; leaf < n_child; ++leaf) out[leaf * data_dim + data_dim - 1] = h.sigma[leaf];
             h.data = h.decoded.data();
         } else {
             const rtohost::NpyArray& d = need("data");
-            h.capacity = (int)d.shape[0];
             if (d.word_size != 2) throw std::runtime_error("data must be stored in half precision");
+            expect(d, "data", {cap, N, N, N, data_dim}, 2);
             h.data = d.bytes.data();
         }
     }
@@ -382,14 +404,17 @@ class Denoiser final {
         rto_check(rto_net_create(&net_, z["w1"].bytes.data(), z["b1"].bytes.data(), z["w2"].bytes.data(), z["b2"].bytes.data(),
                                  in_ch, mid, levels),
                   "rto_net_create");
+        levels_ = levels;
     }
     Denoiser(const Denoiser&) = delete;
     ~Denoiser() { rto_net_destroy(net_); }
     void denoise(const Camera&, RenderContext& ctx, void* stream) { rto_check(rto_denoise(ctx.handle, net_, stream), "denoise"); }
     rto_net* handle() { return net_; }
+    int levels() const { return levels_; }   // filter levels L: the tile split renders a halo of 2 + L rows per band
 
    private:
     rto_net* net_ = nullptr;
+    int levels_ = 4;
 };
 
 }  // namespace volrend

@@ -192,6 +192,76 @@ def test_llff_recentring_bit_exact_vs_reference_code(cli, tmp_path, seed):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs diff %g" % np.abs(got - want).max()
 
 
+def test_malformed_tree_files_are_rejected(cli, tmp_path, capi):
+    """Arrays whose shapes disagree with `child` (truncated / inconsistent tree.npz) are refused by BOTH loaders before any
+    upload: the C ABI takes raw pointers, so the host layer is the only place that can see the lengths."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=3, seed=2)
+    cap = tree["child"].shape[0]
+    pj = str(tmp_path / "t.json")
+    S.write_blender_json(pj, S.make_poses(2))
+    bad = {
+        "short_data": dict(tree, data=tree["data"][: cap - 1]),
+        "wrong_dim": dict(tree, data=tree["data"][..., :27]),
+        "child_shape": dict(tree, child=tree["child"].reshape(cap, 2, 4, 1)),
+    }
+    rs = np.random.default_rng(0)
+    q = {k: tree[k] for k in ("data_dim", "data_format", "invradius3", "offset", "child")}
+    q["quant_colors"] = rs.normal(size=(8, 65536, 3)).astype(np.float16)
+    q["quant_map"] = rs.integers(0, 65536, size=(8, cap, 2, 2, 2)).astype(np.uint16)
+    q["sigma"] = np.ascontiguousarray(tree["data"][..., -1])
+    q["data_retained"] = rs.normal(size=(1, cap, 2, 2, 2, 3)).astype(np.float16)
+    bad["short_map"] = dict(q, quant_map=q["quant_map"][:, : cap - 1])
+    bad["short_sigma"] = dict(q, sigma=q["sigma"][: cap - 1])
+    bad["short_retained"] = dict(q, data_retained=q["data_retained"][:, : cap - 2])
+    bad["small_codebook"] = dict(q, quant_colors=q["quant_colors"][:, :4096])
+    for name, z in bad.items():
+        npz = str(tmp_path / (name + ".npz"))
+        np.savez(npz, **z)
+        r = subprocess.run([cli, npz, pj, "--dry_run"], capture_output=True, text=True)
+        assert r.returncode != 0 and ("malformed tree.npz" in r.stderr or "child must be" in r.stderr), (name, r.stderr[-300:])
+        with pytest.raises(ValueError, match="malformed tree.npz"):
+            capi.N3Tree(npz)
+    ok = str(tmp_path / "ok.npz")
+    np.savez(ok, **q)
+    assert subprocess.run([cli, ok, pj, "--dry_run"], capture_output=True, text=True).returncode == 0
+
+
+def test_npz_reader_rejects_corrupt_archives(cli, tmp_path):
+    """Crafted / truncated zip and npy structures must raise, never read out of bounds (host/npz.cpp)."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=3, seed=2)
+    good = str(tmp_path / "g.npz")
+    S.write_tree_npz(good, tree)
+    raw = bytearray(open(good, "rb").read())
+    pj = str(tmp_path / "t.json")
+    S.write_blender_json(pj, S.make_poses(2))
+    eocd = raw.rfind(b"PK\x05\x06")
+    cd = int.from_bytes(raw[eocd + 16:eocd + 20], "little")
+    cases = {}
+    cases["truncated"] = raw[: len(raw) // 2]
+    c = bytearray(raw); c[cd + 28:cd + 30] = (0xFFFF).to_bytes(2, "little"); cases["name_len"] = c        # name runs past the end
+    c = bytearray(raw); c[cd + 30:cd + 32] = (0xFFF0).to_bytes(2, "little"); cases["extra_len"] = c       # extra field runs past the end
+    c = bytearray(raw); c[eocd + 16:eocd + 20] = (0xFFFFFF00).to_bytes(4, "little"); cases["cd_off"] = c  # directory offset out of range
+    c = bytearray(raw); c[cd + 42:cd + 46] = (len(raw) - 8).to_bytes(4, "little"); cases["lho"] = c        # local header at the very end
+    for name, blob in cases.items():
+        f = str(tmp_path / (name + ".npz"))
+        open(f, "wb").write(bytes(blob))
+        r = subprocess.run([cli, f, pj, "--dry_run"], capture_output=True, text=True)
+        assert r.returncode not in (0, -11, 139), (name, r.returncode, r.stderr[-300:])   # an error, not a crash
+    # npy header whose shape product overflows size_t
+    hdr = "{'descr': '<f2', 'fortran_order': False, 'shape': (4294967296, 4294967296, 8), }"
+    hdr = hdr + " " * (118 - len(hdr) - 1) + "\n"
+    npy = b"\x93NUMPY\x01\x00" + len(hdr).to_bytes(2, "little") + hdr.encode() + b"\0" * 64
+    root = tmp_path / "llff"
+    (root / "images_4").mkdir(parents=True)
+    open(str(root / "poses_bounds.npy"), "wb").write(npy)
+    r = subprocess.run([cli, good, str(root / "poses_bounds.npy"), "--dataset", "llff", "--dry_run"], capture_output=True, text=True)
+    assert r.returncode not in (0, -11, 139), (r.returncode, r.stderr[-300:])
+
+
 def test_dry_run_quantized_tree(cli, tmp_path, capi):
     """svox-compressed variant (scripts/compress_octree.py:68-119): quant_colors/quant_map/sigma/data_retained decoded by
     the C++ loader exactly like the reference loop (n3tree.cpp:279-340) == the Python mirror."""
@@ -370,6 +440,30 @@ def test_cli_pipeline_matches_serial(cli, tmp_path, mid_tree, net_weights, mode,
     # timing-only mode with the device->host copy inside the loop
     t = subprocess.run([cli, *common, "--pipe", "4", "--readback", "rgba8"], capture_output=True, text=True, timeout=600)
     assert t.returncode == 0 and "FPS:" in t.stdout, t.stderr[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("denoise", [True, False])
+def test_cli_tile_split_matches_full_frame(cli, tmp_path, mid_tree, net_weights, capi, denoise):
+    """--tile_split: every frame cut into row bands over the shards (one host thread each), band + halo rendered and denoised
+    per shard, the filter / render epilogue storing the band into the first shard's image through the peer mapping.  The
+    assembled PNGs and float images are byte-identical to the single-GPU serial run.  On a 1-GPU box the shards share
+    device 0 (--gpu_list 0,0,0); with >= 2 GPUs the stores cross NVLink (--num_gpus)."""
+    common = _cli_job(tmp_path, mid_tree, net_weights, n_poses=4, denoise=denoise) + ["--write_float"]
+    a = str(tmp_path / "serial")
+    r = subprocess.run([cli, *common, "-o", a], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    runs = {"list000": ["--gpu_list", "0,0,0"], "list00": ["--gpu_list", "0,0"]}
+    n = capi.device_count()
+    if n >= 2:
+        runs["multi"] = ["--num_gpus", str(min(n, 8))]
+    names = ["img_r_%d.bin" % i for i in range(4)] + ["r_%d.png" % i for i in range(4)]
+    for k, extra in runs.items():
+        b = str(tmp_path / k)
+        u = subprocess.run([cli, *common, "-o", b, "--tile_split", *extra], capture_output=True, text=True, timeout=600)
+        assert u.returncode == 0, u.stderr[-1500:]
+        assert "tile split:" in u.stdout and "latency: median" in u.stdout
+        _same_files(a, b, names)
 
 
 def _llff_dataset(root, n=5):

@@ -33,6 +33,10 @@ def test_tile_bands_and_halo():
                 y0, y1 = SH.render_rows_for_band(b, H, denoise=True)
                 assert y0 == max(0, b[0] - 6) and y1 == min(H, b[1] + 6)
                 assert SH.render_rows_for_band(b, H, denoise=False) == b
+                # the halo follows the net: 2 rows for the two 3x3 convolutions + one per filter level
+                for L in (1, 4, 6):
+                    assert SH.render_rows_for_band(b, H, True, levels=L) == (max(0, b[0] - 2 - L), min(H, b[1] + 2 + L))
+    assert SH.denoise_halo(4) == SH.DENOISE_HALO == 6 and SH.denoise_halo(6) == 8
 
 
 def _worker(rank, world, port, H, W, out):
@@ -64,5 +68,67 @@ def test_gather_bands_gloo_world2(H):
         p.start()
     for p in procs:
         p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
+
+
+def _peer_worker(rank, world, port, out, denoise):
+    """One rank of the peer-store tile split; both ranks share cuda:0 (the IPC mapping works between processes on one
+    device exactly as between devices), the completion barrier goes through gloo."""
+    import numpy as np
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rt_octree_b200 import capi, synthetic as S
+
+    torch.cuda.set_device(0)
+    capi.set_device(0)
+    tree = S.make_tree(depth=7, shell=1.0, halo=0.1, seed=0)
+    W, H = 200, 151
+    fx = S.blender_focal(W)
+    poses = S.poses_to_c2w12(S.make_poses(8))
+    t = capi.N3Tree(tree)
+    net = capi.Denoiser(S.make_guidance_weights(0))
+    cam = capi.Camera(W, H, fx, fx)
+    opt = capi.RenderOptions()
+    opt.spp, opt.denoise = 6, denoise
+    ts = SH.PeerTileSplit(capi, dist, rank, world, W, H, net.levels)
+    ok = True
+    for f in (2, 5):
+        ts.render(t, net, cam, opt, poses[f], f)
+        dist.barrier()
+        if rank == 0:
+            got, got8 = ts.ctx.read_image().copy(), ts.ctx.read_image_rgba8().copy()
+            c1 = capi.RenderContext(W, H)
+            cam.transform = poses[f]
+            c1.rng_set_frame(f)
+            capi.launch_renderer(t, cam, opt, c1)
+            if denoise:
+                net.denoise(cam, c1)
+            ok = ok and bool(np.array_equal(c1.read_image(), got)) and bool(np.array_equal(c1.read_image_rgba8(), got8))
+            ok = ok and got[..., :3].min() < 0.9
+            c1.close()
+        dist.barrier()
+    if rank == 0:
+        out.put(ok)
+    ts.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("denoise", [True, False])
+def test_peer_store_tile_split_two_processes(denoise):
+    """Tile split with peer-direct stores between two PROCESSES (CUDA IPC mapping of rank 0's image; here both on cuda:0,
+    on a multi-GPU box tools/tile_split_check.py runs it over NVLink): the frame assembled in rank 0's buffers by the two
+    bands' own filter epilogues equals the single-context frame bit for bit, float image and RGBA8 copy."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90) + (1 if denoise else 0)
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q, denoise)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Multi-GPU check (run under torchrun, one rank per GPU): single-frame TILE SPLIT over N GPUs with one NCCL gather
-(rt_octree_b200/sharding.py) reproduces the single-GPU frame bit for bit, and reports the single-frame latency.
+"""Multi-GPU check (run under torchrun, one rank per GPU): single-frame TILE SPLIT over N GPUs (rt_octree_b200/sharding.py)
+reproduces the single-GPU frame bit for bit, and reports the single-frame latency of both exchange schemes: the filter
+epilogue's peer-direct stores into rank 0's image (PeerTileSplit, the product path) and one NCCL gather of the bands.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/tile_split_check.py --width 3840 --height 2160
@@ -73,9 +74,15 @@ def main():
             same = bool(torch.equal(full.cpu(), ref))
             ok &= same
             ctx1.close()
+    peer = None
+    if world > 1:
+        peer = SH.bench_tile_split(capi, torch, dist, tree, S.make_guidance_weights(0), poses, rank, world, local, frames=a.frames,
+                                   width=W, height=H)
+        ok &= bool(peer["bit_identical_to_single_gpu"]) if rank == 0 else True
     if rank == 0:
         print(json.dumps({"tile_split": {"n_gpus": world, "width": W, "height": H, "frames": a.frames, "bit_identical_to_single_gpu": ok,
-                                         "latency_ms_median": float(np.median(lat[1:]) * 1e3), "gather_bytes_per_rank": int(H // world * W * 16)}}))
+                                         "gather_latency_ms_median": float(np.median(lat[1:]) * 1e3),
+                                         "gather_bytes_per_rank": int(H // world * W * 16), "peer_store": peer}}))
     if world > 1:
         dist.destroy_process_group()
     sys.exit(0 if ok else 1)

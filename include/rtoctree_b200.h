@@ -127,9 +127,13 @@ int rto_tree_create_quantized(rto_tree** out, const int32_t* child, int64_t capa
                               int n_retained);
 /* Copy one device plane of the loaded tree back to the host (inspection / parity tests; the reference keeps the host
  * arrays in N3Tree::data_ / child_ instead).  `bytes` must equal the plane size: nodes = rto_tree_info.node_bytes,
- * payload = payload_bytes, grid top = 4 << (3*grid_level), grid bricks = n_bricks * 2048, byte bricks = n_bricks * 512. */
+ * payload = payload_bytes, grid top / leaf top = 4 << (3*grid_level), grid bricks / leaf bricks = n_bricks * 2048,
+ * byte bricks = n_bricks * 512 (the leaf planes hold 0 bytes when they were not built). */
 typedef enum rto_tree_plane { RTO_PLANE_NODES = 0, RTO_PLANE_PAYLOAD = 1, RTO_PLANE_GRID_TOP = 2, RTO_PLANE_GRID_BRICKS = 3,
-                              RTO_PLANE_GRID_BRICKS8 = 4 } rto_tree_plane;
+                              RTO_PLANE_GRID_BRICKS8 = 4,
+                              RTO_PLANE_GRID_LEAF_TOP = 5,    /* u32 per level-K cell: flat leaf index (node*8+octant) of a leaf cell */
+                              RTO_PLANE_GRID_LEAF_BRICKS = 6  /* u32 per brick cell: flat leaf index of the covering leaf */
+} rto_tree_plane;
 int rto_tree_read_plane(const rto_tree* tree, int plane, void* host_dst, size_t bytes);
 /* main_headless.cpp:400-405 / n3tree.hpp:69-71: NDC warp for forward-facing (llff) scenes; width<=0 disables. */
 int rto_tree_set_ndc(rto_tree* tree, float ndc_width, float ndc_height, float ndc_focal);

@@ -316,7 +316,7 @@ class N3Tree:
                                      self.data_dim, self.format, self.basis_dim, off, sc))
 
     PLANES = {"nodes": (0, np.uint32), "payload": (1, np.float16), "grid_top": (2, np.uint32), "grid_bricks": (3, np.uint32),
-              "grid_bricks8": (4, np.uint8)}
+              "grid_bricks8": (4, np.uint8), "grid_leaf_top": (5, np.uint32), "grid_leaf_bricks": (6, np.uint32)}
 
     def read_plane(self, name):
         """Device plane copied back to the host (rto_tree_read_plane): nodes / payload / grid_top / grid_bricks."""
@@ -325,7 +325,9 @@ class N3Tree:
         nbytes = {"nodes": i.node_bytes, "payload": i.payload_bytes,
                   "grid_top": (4 << (3 * i.grid_level)) if i.grid_level else 0,
                   "grid_bricks": i.n_bricks * 2048 if i.grid_level else 0,
-                  "grid_bricks8": i.n_bricks * 512 if i.grid_level else 0}[name]
+                  "grid_bricks8": i.n_bricks * 512 if i.grid_level else 0,
+                  "grid_leaf_top": (4 << (3 * i.grid_level)) if i.grid_level else 0,
+                  "grid_leaf_bricks": i.n_bricks * 2048 if i.grid_level else 0}[name]
         out = np.empty(nbytes // np.dtype(dt).itemsize, dt)
         _check(load().rto_tree_read_plane(self._h, which, out.ctypes.data, nbytes))
         return out

@@ -29,6 +29,8 @@ struct rto_tree {
     uint32_t* grid_top = nullptr;      // sparse brick grid (rto_ray.cuh GridDev), optional
     uint32_t* grid_bricks = nullptr;
     uint8_t* grid_bricks8 = nullptr;   // byte plane of the bricks (depth | dense flag)
+    uint32_t* grid_leaf_top = nullptr;     // leaf-id planes: flat leaf index per level-K cell / per brick cell
+    uint32_t* grid_leaf_bricks = nullptr;
     int grid_K = 0;
     int64_t n_bricks = 0;
     rto_tree_info info{};
@@ -194,6 +196,7 @@ static int tree_from_source(rto_tree** out, const rto::TreeSource& src, int N, i
     }
     t->nodes = b.nodes; t->payload = b.payload;
     t->grid_top = b.grid_top; t->grid_bricks = b.grid_bricks; t->grid_bricks8 = b.grid_bricks8;
+    t->grid_leaf_top = b.grid_leaf_top; t->grid_leaf_bricks = b.grid_leaf_bricks;
     t->grid_K = b.grid_K; t->n_bricks = b.n_bricks;
     const int64_t n_entries = src.capacity * 8;
     rto_tree_info& I = t->info;
@@ -204,7 +207,8 @@ static int tree_from_source(rto_tree** out, const rto::TreeSource& src, int N, i
     I.payload_stride_halfs = b.stride;
     I.grid_level = t->grid_K;
     I.n_bricks = t->n_bricks;
-    I.grid_bytes = t->grid_K ? (int64_t)((((size_t)1 << (3 * t->grid_K)) + (size_t)t->n_bricks * 512) * sizeof(uint32_t) + (size_t)t->n_bricks * 512) : 0;
+    I.grid_bytes = t->grid_K ? (int64_t)((((size_t)1 << (3 * t->grid_K)) + (size_t)t->n_bricks * 512) * sizeof(uint32_t) * (t->grid_leaf_top ? 2 : 1) +
+                                         (size_t)t->n_bricks * 512) : 0;
     for (int i = 0; i < 3; ++i) { I.offset[i] = offset[i]; I.scale[i] = scale[i]; }
     I.ndc_width = -1.f; I.ndc_height = 0.f; I.ndc_focal = 0.f;
     *out = t;
@@ -250,6 +254,8 @@ int rto_tree_read_plane(const rto_tree* t, int plane, void* host_dst, size_t byt
         case RTO_PLANE_GRID_TOP: src = t->grid_top; have = t->grid_K ? ((size_t)1 << (3 * t->grid_K)) * sizeof(uint32_t) : 0; break;
         case RTO_PLANE_GRID_BRICKS: src = t->grid_bricks; have = t->grid_K ? (size_t)t->n_bricks * 512 * sizeof(uint32_t) : 0; break;
         case RTO_PLANE_GRID_BRICKS8: src = t->grid_bricks8; have = t->grid_K ? (size_t)t->n_bricks * 512 : 0; break;
+        case RTO_PLANE_GRID_LEAF_TOP: src = t->grid_leaf_top; have = t->grid_leaf_top ? ((size_t)1 << (3 * t->grid_K)) * sizeof(uint32_t) : 0; break;
+        case RTO_PLANE_GRID_LEAF_BRICKS: src = t->grid_leaf_bricks; have = t->grid_leaf_top ? (size_t)t->n_bricks * 512 * sizeof(uint32_t) : 0; break;
         default: return fail(RTO_ERR_INVALID, "unknown plane %d", plane);
     }
     if (bytes != have) return fail(RTO_ERR_INVALID, "plane %d holds %zu bytes, caller asked for %zu", plane, have, bytes);
@@ -274,6 +280,8 @@ void rto_tree_destroy(rto_tree* t) {
     cudaFree(t->grid_top);
     cudaFree(t->grid_bricks);
     cudaFree(t->grid_bricks8);
+    cudaFree(t->grid_leaf_top);
+    cudaFree(t->grid_leaf_bricks);
     delete t;
 }
 
@@ -419,7 +427,8 @@ static int fill_render_args(rto_context* c, const rto_tree* t, const rto_camera*
     fp.step_size = opt->step_size; fp.sigma_thresh = opt->sigma_thresh; fp.background = opt->background_brightness;
     fp.W = c->W; fp.H = c->H;
     a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth,
-                          rto::make_grid_dev(t->grid_top, t->grid_bricks, t->grid_K, t->grid_bricks8), (size_t)t->n_bricks * 512 * sizeof(uint32_t)};
+                          rto::make_grid_dev(t->grid_top, t->grid_bricks, t->grid_K, t->grid_bricks8, t->grid_leaf_top, t->grid_leaf_bricks),
+                          (size_t)t->n_bricks * 512 * sizeof(uint32_t)};
     a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
     a.aux = c->aux;

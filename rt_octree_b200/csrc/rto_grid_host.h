@@ -59,6 +59,40 @@ inline bool build_grid_host(const int32_t* child, const uint16_t* data, int data
     return true;
 }
 
+// leaf-id planes (rto_ray.cuh GridDev::leaf_top / leaf_bricks) from the tree itself: every level-K cell and every finest-level
+// cell of a brick is located by a plain descent from the root, independently of how `top` / `bricks` were filled.
+inline void build_grid_leaf_host(const int32_t* child, int K, const std::vector<uint32_t>& top, size_t n_bricks,
+                                 std::vector<uint32_t>& leaf_top, std::vector<uint32_t>& leaf_bricks) {
+    const size_t S = (size_t)1 << K;
+    leaf_top.assign(S * S * S, 0u);
+    leaf_bricks.assign((n_bricks ? n_bricks : 1) * 512, 0u);
+    for (uint32_t x = 0; x < S; ++x)
+        for (uint32_t y = 0; y < S; ++y)
+            for (uint32_t z = 0; z < S; ++z) {
+                const size_t t = (((size_t)x << K) | y) << K | z;
+                int64_t node = 0;
+                bool leaf = false;
+                for (int d = 1; d <= K && !leaf; ++d) {
+                    const int sh = K - d;
+                    const int64_t e = node * 8 + ((((x >> sh) & 1u) << 2) | (((y >> sh) & 1u) << 1) | ((z >> sh) & 1u));
+                    if (child[e] == 0) { leaf_top[t] = (uint32_t)e; leaf = true; }
+                    else node += child[e];
+                }
+                if (leaf) continue;
+                uint32_t* out = leaf_bricks.data() + (size_t)top[t] * 512;
+                for (uint32_t c = 0; c < 512; ++c) {
+                    const uint32_t lx = c >> 6, ly = (c >> 3) & 7u, lz = c & 7u;
+                    int64_t n2 = node;
+                    for (int j = 1; j <= 3; ++j) {
+                        const int sh = 3 - j;
+                        const int64_t e = n2 * 8 + ((((lx >> sh) & 1u) << 2) | (((ly >> sh) & 1u) << 1) | ((lz >> sh) & 1u));
+                        if (child[e] == 0) { out[c] = (uint32_t)e; break; }
+                        n2 += child[e];
+                    }
+                }
+            }
+}
+
 // byte plane of the bricks (rto_ray.cuh brick_byte): depth | 0x80 where sigma is non-zero
 inline void grid_bytes_host(const std::vector<uint32_t>& bricks, std::vector<uint8_t>& bricks8) {
     bricks8.resize(bricks.size());

@@ -26,7 +26,12 @@ namespace rto {
 #define RTO_RENDER_MIN_BLOCKS 10  // __launch_bounds__ min blocks/SM of the production kernels (10 -> 48 registers, no spill in the loop)
 #endif
 
-constexpr int kTileW = 8, kTileH = 4;      // pixels per warp-tile
+#ifndef RTO_TILE_W
+#define RTO_TILE_W 8
+#define RTO_TILE_H 4
+#endif
+constexpr int kTileW = RTO_TILE_W, kTileH = RTO_TILE_H;      // pixels per warp-tile (8x4 = one lane per pixel; smaller tiles leave
+                                                             // lanes idle: a diagnostic of the lock-step cost, tools/tile_log.py)
 #ifndef RTO_BLOCK_WARPS
 #define RTO_BLOCK_WARPS 4            // warps per block = warp tiles per super-tile (4: 2x2 tiles = 16x8 px, 8: 4x2 = 32x8 px)
 #endif
@@ -53,6 +58,22 @@ struct SmemRay {
     __device__ __forceinline__ float& scratch(int i) { return reinterpret_cast<float*>(base)[(off_dst + 3 * SPP + 1 + i) * kBlockThreads]; }
     static __host__ __device__ int words(int max_depth) { return max_depth + 1 + 3 * SPP + 1 + 2; }   // max_depth = -1: no stack
 };
+
+#ifdef RTO_TILE_LOG
+// Diagnostic build only (tools/build_variant.sh tilelog "-DRTO_TILE_LOG"): every warp tile logs
+// {tile id, SM id, start ns, end ns, max steps over its lanes, sum of steps, marching-loop ns, hits} into rto_tile_log.
+__device__ unsigned long long* rto_tile_log = nullptr;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+    return r;
+}
+#endif
 
 // Persistent kernel.  Work unit = a 16x8 pixel SUPER-TILE (2x2 warp tiles) claimed by a block from a global counter
 // (centre rows first); the block's warps pull the four 8x4 warp tiles of the current super-tile from a shared-memory
@@ -82,8 +103,9 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
 }
 
 // GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent.
-// GRID: 0 = tree walker, 1 = brick grid read through the 4-byte leaf words, 2 = brick grid read through the byte plane
-// (production; RTO_GRID8=0 selects 1 for A/B runs).
+// GRID: 0 = tree walker, 1 = brick grid read through the 4-byte leaf words, 2 = brick grid read through the byte plane,
+// 3 = byte plane + collisions resolved through the leaf-id planes after the march (production; RTO_GRID8=0 selects 1 and
+// RTO_DEFER_HITS=0 selects 2 for A/B runs).
 // TRACE: write the per-ray traversal record (rto_trace).  TRACE && GRID is the PRODUCTION marcher with the record switched
 // on: steps / term / src / t / hits come straight out of walk_grid, and the visited-leaf sequence is produced by locating
 // every sample point in the tree as well (walk_grid<VERIFY>), which also cross-checks the grid's depth and sigma per step.
@@ -114,7 +136,12 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
         const int tc = sc * kSuperX + (sub % kSuperX), row = srow * kSuperY + (sub / kSuperX);
         const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
         const int iy = a.y0 + row * kTileH + (lane / kTileW);
-        if (ix < a.x1 && iy < a.y1) {
+#ifdef RTO_TILE_LOG
+        const unsigned long long log_t0 = gtime_ns();
+        unsigned log_steps = 0, log_hits = 0;
+        unsigned long long log_t1 = log_t0, log_t2 = log_t0;
+#endif
+        if (ix < a.x1 && iy < a.y1 && lane < kTileW * kTileH) {
             const int idx = iy * fp.W + ix;   // full-frame pixel index: RNG offset and buffer address (volrend.cu:92-95)
             RaySetup rs;
             setup_ray(fp, ix, iy, rs);
@@ -132,11 +159,20 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             auto sink = [&](uint32_t step, uint32_t leaf) {
                 if (a.tr.leaf_seq && (int)step < a.tr.max_seq) a.tr.leaf_seq[(size_t)idx * a.tr.max_seq + step] = (int32_t)leaf;
             };
+#ifdef RTO_TILE_LOG
+            log_t1 = gtime_ns();
+#endif
             if constexpr (GRID != 0)
-                walk_grid<SPP, TRACE, GRID == 2>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+                walk_grid<SPP, TRACE, GRID >= 2, GRID == 3>(nodes, a.tree.grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             else
                 walk<SPP, TRACE>(nodes, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             const uint32_t sh_nums = wo.n_hits;
+            if constexpr (GRID == 3) resolve_hits<SPP>(a.tree.grid, mem, sh_nums);   // cell references -> leaf indices, all lanes together
+#ifdef RTO_TILE_LOG
+            log_t2 = gtime_ns();
+            log_steps = wo.steps;
+            log_hits = wo.n_hits;
+#endif
 
             if (TRACE) {
                 const TraceOut& tr = a.tr;
@@ -242,6 +278,24 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             if (a.img8) RTO_ST(a.img8 + idx, rgba8_of(out0, out1, out2, 1.0f));
         }
         __syncwarp();
+#ifdef RTO_TILE_LOG
+        if (rto_tile_log) {
+            unsigned mx = log_steps, sm = log_steps, hs = log_hits;
+            unsigned long long t1 = log_t1, t2 = log_t2;
+            for (int o = 16; o; o >>= 1) {
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                hs += __shfl_xor_sync(0xffffffffu, hs, o);
+                t1 = min(t1, __shfl_xor_sync(0xffffffffu, t1, o));
+                t2 = max(t2, __shfl_xor_sync(0xffffffffu, t2, o));
+            }
+            if (lane == 0) {
+                unsigned long long* q = rto_tile_log + (size_t)(sid * kBlockWarps + sub) * 8;
+                q[0] = (unsigned long long)(sid * kBlockWarps + sub); q[1] = smid(); q[2] = log_t0; q[3] = gtime_ns();
+                q[4] = mx; q[5] = sm; q[6] = t2 - t1; q[7] = hs;
+            }
+        }
+#endif
     }
     // the last warp to leave re-arms the counters for the next launch on this context
     if (lane == 0) {
@@ -273,7 +327,9 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     const bool grid_path = trace != 1 && a.tree.grid.K > 0;
     const char* g8 = getenv("RTO_GRID8");   // read per launch so that one process can A/B the two planes
     const bool grid8 = grid_path && !(g8 && g8[0] == '0') && a.tree.grid.bricks8 != nullptr;
-    const int v = (trace ? 3 : 0) + (grid_path ? (grid8 ? 2 : 1) : 0);
+    const char* dh = getenv("RTO_DEFER_HITS");
+    const bool defer = grid8 && !(dh && dh[0] == '0') && a.tree.grid.leaf_top != nullptr;
+    const int v = (trace ? 4 : 0) + (grid_path ? (grid8 ? (defer ? 3 : 2) : 1) : 0);
     const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
     // Function attributes, occupancy and the L2 set-aside are per DEVICE, so the cached launch state is indexed by the
     // current device; the one-time set-up of a slot runs under that slot's mutex (several host threads may drive the same
@@ -281,8 +337,8 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     struct DevState {
         std::mutex mu;
         int num_sms = 0;
-        size_t smem_set[6] = {0, 0, 0, 0, 0, 0};
-        int occ_limit[6] = {0, 0, 0, 0, 0, 0};
+        size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int occ_limit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int persist = -1, max_win = 0, max_persist = 0;
         size_t persist_set = 0;   // current cudaLimitPersistingL2CacheSize this library asked for on the device
     };
@@ -291,8 +347,9 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevState& ds = dev_state[dev >= 0 && dev < kMaxDevices ? dev : 0];
-    void (*kern)(RenderArgs) = trace ? (grid8 ? render_kernel<SPP, true, 2> : (grid_path ? render_kernel<SPP, true, 1> : render_kernel<SPP, true, 0>))
-                                     : (grid8 ? render_kernel<SPP, false, 2> : (grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>));
+    void (*kern)(RenderArgs) =
+        trace ? (defer ? render_kernel<SPP, true, 3> : grid8 ? render_kernel<SPP, true, 2> : grid_path ? render_kernel<SPP, true, 1> : render_kernel<SPP, true, 0>)
+              : (defer ? render_kernel<SPP, false, 3> : grid8 ? render_kernel<SPP, false, 2> : grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>);
     std::unique_lock<std::mutex> lock(ds.mu);
     if (smem > ds.smem_set[v] || ds.occ_limit[v] == 0) {   // first launch on this device, or a deeper tree than any seen before
         if ((e = cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -355,6 +412,13 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     kern<<<grid, kBlockThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
+
+#ifdef RTO_TILE_LOG
+extern "C" int rto_debug_set_tile_log(void* dev_ptr) {
+    unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+    return cudaMemcpyToSymbol(rto_tile_log, &p, sizeof p) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 // SPP dispatch = the reference's instantiation list (volrend.cu:266-278); anything else is an error there too.
 cudaError_t launch_render(const RenderArgs& a, int spp, int trace, cudaStream_t stream, bool* bad_spp) {

@@ -19,6 +19,8 @@
 //   grid_scan_kernel              per-block brick counts  -> exclusive offsets
 //   grid_assign_kernel            ids in the host builder's order -> top table brick ids, brick -> node map
 //   grid_brick_kernel             nodes                   -> bricks (leaf words) + byte bricks (depth | dense flag)
+//   grid_leaf_top_kernel          nodes + top             -> leaf-id plane of the level-K cells, level-K node of every brick
+//   grid_leaf_brick_kernel        nodes                   -> leaf-id plane of the brick cells
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -246,6 +248,43 @@ __global__ void grid_brick_kernel(const uint32_t* __restrict__ nodes, const uint
     bricks8[(size_t)b * 512 + c] = brick_byte(out);
 }
 
+// Leaf-id planes (rto_ray.cuh GridDev::leaf_top / leaf_bricks), derived from the node words and the finished top table
+// only — whichever builder filled the grid.  Thread t = level-K cell (x-major index, as the marcher forms it): a leaf
+// reached within K look-ups gives leaf_top[t]; otherwise top[t] is the cell's brick id and the level-K node is noted for
+// the brick pass, which descends at most 3 more levels per finest-level cell.
+__global__ void grid_leaf_top_kernel(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ top, int K,
+                                     uint32_t n_cells, uint32_t* __restrict__ leaf_top, uint32_t* __restrict__ brick_node) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_cells) return;
+    const uint32_t mask = (1u << K) - 1u;
+    const uint32_t x = t >> (2 * K), y = (t >> K) & mask, z = t & mask;
+    uint32_t node = 0u;
+    for (int d = 1; d <= K; ++d) {
+        const int sh = K - d;
+        const uint32_t e = node * 8u + ((((x >> sh) & 1u) << 2) | (((y >> sh) & 1u) << 1) | ((z >> sh) & 1u));
+        const uint32_t word = nodes[e];
+        if (word & RTO_LEAF_FLAG) { leaf_top[t] = e; return; }
+        node = word;
+    }
+    leaf_top[t] = 0u;
+    brick_node[top[t]] = node;
+}
+__global__ void grid_leaf_brick_kernel(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ brick_node,
+                                       uint32_t* __restrict__ leaf_bricks) {
+    const uint32_t c = threadIdx.x;   // == brick_cell_index(lx, ly, lz)
+    const uint32_t lx = c >> 6, ly = (c >> 3) & 7u, lz = c & 7u;
+    uint32_t node = brick_node[blockIdx.x];
+    uint32_t out = 0u;
+    for (int j = 1; j <= 3; ++j) {
+        const int sh = 3 - j;
+        const uint32_t e = node * 8u + ((((lx >> sh) & 1u) << 2) | (((ly >> sh) & 1u) << 1) | ((lz >> sh) & 1u));
+        const uint32_t word = nodes[e];
+        if (word & RTO_LEAF_FLAG) { out = e; break; }
+        node = word;
+    }
+    leaf_bricks[(size_t)blockIdx.x * 512 + c] = out;
+}
+
 // --------------------------------------------------------------------------------------------------- host driver
 namespace {
 struct DevBuf {   // frees on scope exit unless released
@@ -365,7 +404,33 @@ static int grid_build_host(const TreeSource& s, int max_depth, TreeBuilt& out, c
     return RTO_OK;
 }
 
+// leaf-id planes for a finished grid (either builder).  Skipped (planes stay nullptr, collisions then descend the tree) when
+// the brick-cell reference would not fit 31 bits, or with RTO_LEAF_PLANES=0.
+static int grid_leaf_build_device(const uint32_t* nodes, TreeBuilt& out, int64_t* launches, const Fail& fail) {
+    const char* off = getenv("RTO_LEAF_PLANES");
+    if (out.grid_K <= 0 || out.n_bricks >= ((int64_t)1 << 22) || (off && off[0] == '0')) return RTO_OK;
+    const uint32_t n_cells = 1u << (3 * out.grid_K);
+    const size_t nb = (size_t)(out.n_bricks ? out.n_bricks : 1);
+    DevBuf lt, lb, bn;
+    RTO_TRY(lt.alloc((size_t)n_cells * sizeof(uint32_t)), "cudaMalloc(grid leaf top)");
+    RTO_TRY(lb.alloc(nb * 512 * sizeof(uint32_t)), "cudaMalloc(grid leaf bricks)");
+    RTO_TRY(bn.alloc(nb * sizeof(uint32_t)), "cudaMalloc(grid scratch)");
+    grid_leaf_top_kernel<<<blocks_for(n_cells, 256), 256>>>(nodes, out.grid_top, out.grid_K, n_cells, lt.as<uint32_t>(), bn.as<uint32_t>());
+    RTO_TRY(cudaGetLastError(), "grid_leaf_top_kernel");
+    ++*launches;
+    if (out.n_bricks) {
+        grid_leaf_brick_kernel<<<(unsigned)out.n_bricks, 512>>>(nodes, bn.as<uint32_t>(), lb.as<uint32_t>());
+        RTO_TRY(cudaGetLastError(), "grid_leaf_brick_kernel");
+        ++*launches;
+    }
+    RTO_TRY(cudaDeviceSynchronize(), "grid leaf planes");
+    out.grid_leaf_top = lt.release<uint32_t>();
+    out.grid_leaf_bricks = lb.release<uint32_t>();
+    return RTO_OK;
+}
+
 void tree_built_free(TreeBuilt& b) {
+    cudaFree(b.grid_leaf_top); cudaFree(b.grid_leaf_bricks);
     cudaFree(b.nodes); cudaFree(b.payload); cudaFree(b.grid_top); cudaFree(b.grid_bricks); cudaFree(b.grid_bricks8);
     b = TreeBuilt{};
 }
@@ -446,6 +511,7 @@ int build_tree_device(const TreeSource& s, TreeBuilt& out, std::string& err, int
         int rc;
         if (how && how[0] == 'h' && !quant) rc = grid_build_host(s, depth, out, fail);
         else rc = grid_build_device(nodes.as<uint32_t>(), depth, out, launches, fail);
+        if (rc == RTO_OK) rc = grid_leaf_build_device(nodes.as<uint32_t>(), out, launches, fail);
         if (rc) { tree_built_free(out); return rc; }
     }
     out.nodes = nodes.release<uint32_t>();

@@ -67,6 +67,8 @@ def host_ray_lib():
     lib.host_ray_set_grid.argtypes = [P, P, I, C.c_int64, I, P]
     lib.host_ray_use_byte_bricks.restype = None
     lib.host_ray_use_byte_bricks.argtypes = [I]
+    lib.host_ray_use_deferred_hits.restype = None
+    lib.host_ray_use_deferred_hits.argtypes = [I]
     return lib
 
 

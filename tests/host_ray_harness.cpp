@@ -46,7 +46,10 @@ void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameP
         auto sink = [&](uint32_t step, uint32_t leaf) {
             if (leaf_seq && (int)step < max_seq) leaf_seq[r * max_seq + step] = (int32_t)leaf;
         };
-        if (grid && grid->bricks8)
+        if (grid && grid->bricks8 && grid->leaf_top) {   // production configuration: byte plane + deferred leaf look-up
+            walk_grid<SPP, true, true, true>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
+            resolve_hits<SPP>(*grid, mem, wo.n_hits);
+        } else if (grid && grid->bricks8)
             walk_grid<SPP, true, true>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
         else if (grid)
             walk_grid<SPP, true, false>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
@@ -65,16 +68,25 @@ void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameP
 }
 }  // namespace
 
-static std::vector<uint32_t> g_top, g_bricks;
+static std::vector<uint32_t> g_top, g_bricks, g_leaf_top, g_leaf_bricks;
 static std::vector<uint8_t> g_bricks8;
-static GridDev g_grid{nullptr, nullptr, 0, nullptr};
+static GridDev g_grid{nullptr, nullptr, 0, nullptr, nullptr, nullptr};
 static bool g_grid_on = false;
 static bool g_byte_bricks = true;
+static bool g_defer = true;
 
 // 1 (default): walk_grid reads the byte plane like the production kernel; 0: the 4-byte leaf words (RTO_GRID8=0 variant)
 extern "C" void host_ray_use_byte_bricks(int on) {
     g_byte_bricks = on != 0;
     g_grid.bricks8 = g_byte_bricks && !g_bricks8.empty() ? g_bricks8.data() : nullptr;
+}
+
+// 1 (default): collisions record a cell reference, resolved through the leaf-id planes after the march (production);
+// 0: root descent at every collision
+extern "C" void host_ray_use_deferred_hits(int on) {
+    g_defer = on != 0;
+    g_grid.leaf_top = g_defer && !g_leaf_top.empty() ? g_leaf_top.data() : nullptr;
+    g_grid.leaf_bricks = g_defer && !g_leaf_bricks.empty() ? g_leaf_bricks.data() : nullptr;
 }
 
 // Build (or drop, child == NULL) the sparse brick grid used by subsequent host_ray_walk calls.
@@ -87,7 +99,9 @@ extern "C" int host_ray_set_grid(const int32_t* child, const uint16_t* data, int
     if (!build_grid_host(child, data, data_dim, capacity, max_depth, g_top, g_bricks, K)) return 0;
     if (g_bricks.empty()) g_bricks.assign(512, 0u);
     grid_bytes_host(g_bricks, g_bricks8);
-    g_grid = make_grid_dev(g_top.data(), g_bricks.data(), K, g_byte_bricks ? g_bricks8.data() : nullptr);
+    build_grid_leaf_host(child, K, g_top, g_bricks.size() / 512, g_leaf_top, g_leaf_bricks);
+    g_grid = make_grid_dev(g_top.data(), g_bricks.data(), K, g_byte_bricks ? g_bricks8.data() : nullptr,
+                           g_defer ? g_leaf_top.data() : nullptr, g_defer ? g_leaf_bricks.data() : nullptr);
     g_grid_on = true;
     if (n_bricks) *n_bricks = (int64_t)(g_bricks.size() / 512);
     return K;

@@ -76,6 +76,51 @@ def test_device_grid_bench_tree_equals_host_builder(capi):
     assert np.array_equal(t.read_plane("grid_bricks"), h.read_plane("grid_bricks"))
 
 
+def _leaf_of_cells(tree, level):
+    """numpy: flat leaf index (node*8+octant, the reference's sub_ptr) and leaf depth of every cell of the 2^level grid,
+    by descending all cells at once (n3tree_query.hpp:13-48 on integer coordinates)."""
+    child = tree["child"].reshape(-1).astype(np.int64)
+    S = 1 << level
+    x, y, z = np.meshgrid(np.arange(S), np.arange(S), np.arange(S), indexing="ij")
+    x, y, z = x.reshape(-1), y.reshape(-1), z.reshape(-1)
+    node = np.zeros(x.size, np.int64)
+    leaf = np.full(x.size, -1, np.int64)
+    depth = np.zeros(x.size, np.int64)
+    for d in range(1, level + 1):
+        sh = level - d
+        e = node * 8 + ((((x >> sh) & 1) << 2) | (((y >> sh) & 1) << 1) | ((z >> sh) & 1))
+        live = leaf < 0
+        is_leaf = live & (child[e] == 0)
+        leaf[is_leaf], depth[is_leaf] = e[is_leaf], d
+        go = live & ~is_leaf
+        node[go] = node[go] + child[e[go]]
+    return leaf.reshape(S, S, S), depth.reshape(S, S, S)
+
+
+@pytest.mark.parametrize("depth", [4, 6, 7])
+def test_leaf_id_planes(capi, depth):
+    """Leaf-id planes (what collisions are resolved through after the march): every level-K leaf cell and every brick cell
+    names the leaf a root descent finds, for both grid builders."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=depth, shell=1.0, halo=0.2, seed=40 + depth)
+    K = depth - 3
+    fine_leaf, _ = _leaf_of_cells(tree, depth)
+    coarse_leaf, coarse_depth = _leaf_of_cells(tree, K)
+    for t in (capi.N3Tree(tree), _host_grid_tree(capi, tree)):
+        top = t.read_plane("grid_top").reshape((1 << K,) * 3)
+        lt = t.read_plane("grid_leaf_top").reshape((1 << K,) * 3)
+        lb = t.read_plane("grid_leaf_bricks").reshape(-1, 8, 8, 8)
+        is_leaf = (top & 0x80000000) != 0
+        assert np.array_equal(is_leaf, coarse_depth > 0)
+        assert np.array_equal(lt[is_leaf].astype(np.int64), coarse_leaf[is_leaf])
+        assert is_leaf.any() and (~is_leaf).any() and lb.shape[0] == t.info.n_bricks
+        cx, cy, cz = np.nonzero(~is_leaf)
+        for bx, by, bz in list(zip(cx, cy, cz))[:: max(1, len(cx) // 400)]:      # a few hundred bricks, every cell of each
+            want = fine_leaf[bx * 8:bx * 8 + 8, by * 8:by * 8 + 8, bz * 8:bz * 8 + 8]
+            assert np.array_equal(lb[top[bx, by, bz]].astype(np.int64), want)
+
+
 def test_permuted_node_order_builds_the_same_grid(capi, small_tree):
     """svox files are not breadth-first: shuffle the node numbering (negative relative offsets appear) and check that the
     geometry the grid encodes does not change."""

@@ -77,11 +77,13 @@ def test_empty_and_degenerate_trees(oracle, host_ray_lib, poses8):
             assert o["aux"][3].max() == 1.0
 
 
-@pytest.mark.parametrize("byte_bricks", [True, False])
+@pytest.mark.parametrize("byte_bricks,deferred", [(True, True), (True, False), (False, False)],
+                         ids=["bytes+leaf_planes(production)", "bytes", "words"])
 @pytest.mark.parametrize("spp", [1, 6, 32])
-def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp, byte_bricks):
+def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp, byte_bricks, deferred):
     """The sparse brick grid walker (rto_ray.cuh walk_grid: 1-2 loads per step, no descent) against the oracle; the VERIFY
-    build also checks at every step that the grid's (depth, sigma) equal the tree's (term == -777 flags a mismatch)."""
+    build also checks at every step that the grid's (depth, sigma) equal the tree's, and at every collision that the
+    leaf-id plane names the leaf the root descent finds (term == -777 flags a mismatch)."""
     from rt_octree_b200 import synthetic as S
 
     W, H = 120, 90
@@ -89,7 +91,8 @@ def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp, b
     for pi in (0, 5):
         rng = oracle.frame_rng(pi)
         o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48)
-        h = host_walk(host_ray_lib, mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48, grid=True, byte_bricks=byte_bricks)
+        h = host_walk(host_ray_lib, mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48, grid=True, byte_bricks=byte_bricks,
+                      deferred=deferred)
         assert not (h["term"] == -777).any(), "grid (depth, sigma) disagrees with the tree"
         for k in TRACE_KEYS + ("leaf_seq",):
             assert np.array_equal(h[k], o[k]), (k, spp, pi)

@@ -111,7 +111,7 @@ def _peer_worker(rank, world, port, out, denoise):
             c1.close()
         dist.barrier()
     if rank == 0:
-        out.put(ok)
+        out.put(bool(ok))
     ts.close()
     dist.destroy_process_group()
 

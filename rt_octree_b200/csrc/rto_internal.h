@@ -59,6 +59,19 @@ struct TraceOut {           // all optional (nullptr); indexed by the FULL-FRAME
     int max_seq;
 };
 
+// Latency mode of the render kernel (render_kernel_split, rto_render.cu): global hand-off state for rays that busy warps give
+// to idle ones once the tile queue has run dry.  Device memory owned by the context, all zero between launches.
+constexpr unsigned kSplitPoolRing = 1u << 17;    // ray records (ring); at most 16 per batch in flight x resident warps
+constexpr unsigned kSplitBatchRing = 1u << 15;   // batch descriptors (ring)
+constexpr int kSplitRecWords = 48;               // words per ray record (SPP <= 8: 20 + 3*SPP + 1 <= 45)
+struct SplitQueue {
+    unsigned bq_head, bq_tail, done, reserve;    // one 16-byte line: polled with a single volatile v4 load
+    int waiting;                                 // idle warps waiting for rays, minus batches published but not yet taken
+    int pad[3];
+    unsigned* bq;                                // [kSplitBatchRing] 0 = empty, else 0x80000000 | first record << 4 | count - 1
+    uint32_t* pool;                              // [kSplitPoolRing][kSplitRecWords]
+};
+
 struct RenderArgs {
     FrameParams fp;
     TreeDev tree;
@@ -70,6 +83,7 @@ struct RenderArgs {
     int* tile_counter;             // [2] device ints owned by the context: next tile, finished warps (self re-arming)
     const AdvanceMap* adv_rows;    // [H] pcg32 jump-ahead maps for iy*W*spp
     const AdvanceMap* adv_cols;    // [W] ... for ix*spp
+    SplitQueue* split;             // latency mode (nullptr: off): idle warps take over rays of busy ones while the kernel drains
     TraceOut tr;
 };
 

@@ -102,6 +102,97 @@ __device__ __forceinline__ bool next_tile(unsigned* s_state, int* g_counter, int
     return true;
 }
 
+// Colour of a finished ray from its collided leaves (rt_core.cuh:277-331), background composite (volrend.cu:174-179) and the
+// aux [8][H][W] / image [H][W][4] (/ RGBA8) stores (volrend.cu:187-212).  mem.hit_leaf(i) holds LEAF indices here.
+template <int SPP, class Mem>
+__device__ __forceinline__ void shade_composite_write(const RenderArgs& a, Mem& mem, const float (&vdir)[3], int idx, uint32_t sh_nums) {
+    const FrameParams& fp = a.fp;
+    float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
+    if (sh_nums > 0) {
+        // accumulate colour (rt_core.cuh:277-331)
+        const int bd = a.tree.basis_dim;
+        const __half* __restrict__ sh = a.tree.sh;
+        const int stride = a.tree.sh_stride;
+        if (bd == 9) {
+            float b[9];
+            sh_basis(9, vdir, b);
+            for (int i = 0; i < (int)sh_nums; ++i) {
+                const uint4* q = reinterpret_cast<const uint4*>(sh + (size_t)mem.hit_leaf(i) * stride);
+                const float c_i = mem.hit_cnt(i);
+                uint32_t w[16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 v = __ldg(q + k);
+                    w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                }
+#define HV(k) f_half_bits_to_float((w[(k) >> 1] >> (((k) & 1) * 16)) & 0xffffu)
+                float rgb[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+#define MB(k) (b[k] * HV(9 * c + (k)))
+                    float tmp = b[0] * HV(9 * c);
+                    tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
+                    tmp += MB(1) + MB(2) + MB(3);
+#undef MB
+                    rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
+                }
+#undef HV
+                out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
+                out3 += c_i;
+            }
+        } else if (bd > 0) {
+            float b[25];
+#pragma unroll
+            for (int k = 0; k < 25; ++k) b[k] = 0.f;
+            sh_basis(bd, vdir, b);
+            for (int i = 0; i < (int)sh_nums; ++i) {
+                const float c_i = mem.hit_cnt(i);
+                const __half* h = sh + (size_t)mem.hit_leaf(i) * stride;
+                float rgb[3];
+                for (int c = 0; c < 3; ++c) {
+                    const __half* hc = h + bd * c;
+#define MB(k) (b[k] * __half2float(__ldg(hc + (k))))
+                    float tmp = b[0] * __half2float(__ldg(hc));
+                    if (bd >= 25) tmp += MB(16) + MB(17) + MB(18) + MB(19) + MB(20) + MB(21) + MB(22) + MB(23) + MB(24);
+                    if (bd >= 16) tmp += MB(9) + MB(10) + MB(11) + MB(12) + MB(13) + MB(14) + MB(15);
+                    if (bd >= 9) tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
+                    if (bd >= 4) tmp += MB(1) + MB(2) + MB(3);
+#undef MB
+                    rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
+                }
+                out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
+                out3 += c_i;
+            }
+        } else {  // RGBA leaves (rt_core.cuh:322-326)
+            for (int i = 0; i < (int)sh_nums; ++i) {
+                const float c_i = mem.hit_cnt(i);
+                const __half* h = sh + (size_t)mem.hit_leaf(i) * stride;
+                out0 += __half2float(__ldg(h + 0)) * c_i;
+                out1 += __half2float(__ldg(h + 1)) * c_i;
+                out2 += __half2float(__ldg(h + 2)) * c_i;
+                out3 += c_i;
+            }
+        }
+        constexpr float INV_SPP = 1.0f / SPP;
+        out0 = f_mul(out0, INV_SPP); out1 = f_mul(out1, INV_SPP); out2 = f_mul(out2, INV_SPP); out3 = f_mul(out3, INV_SPP);
+    }
+
+    // background composite, offscreen branch (volrend.cu:174-179)
+    const float remain = f_mul(f_sub(1.f, out3), fp.background);
+    out0 = f_add(out0, remain); out1 = f_add(out1, remain); out2 = f_add(out2, remain);
+
+    // aux [8][H][W] (volrend.cu:187-202) and image [H][W][4] (volrend.cu:205-212)
+    if (a.aux) {
+        const size_t SIZE = (size_t)fp.W * fp.H;
+        float* q = a.aux + idx;
+        RTO_ST(q, out0); RTO_ST(q + SIZE, out1); RTO_ST(q + 2 * SIZE, out2); RTO_ST(q + 3 * SIZE, out3);
+        RTO_ST(q + 4 * SIZE, f_mul(out0, out0)); RTO_ST(q + 5 * SIZE, f_mul(out1, out1));
+        RTO_ST(q + 6 * SIZE, f_mul(out2, out2)); RTO_ST(q + 7 * SIZE, f_mul(out3, out3));
+    }
+    if (a.img) RTO_ST(a.img + idx, make_float4(out0, out1, out2, 1.0f));
+    if (a.img8) RTO_ST(a.img8 + idx, rgba8_of(out0, out1, out2, 1.0f));
+}
+
 // GRID: march over the sparse brick grid (rto_ray.cuh walk_grid) instead of the ancestor-stack descent.
 // GRID: 0 = tree walker, 1 = brick grid read through the 4-byte leaf words, 2 = brick grid read through the byte plane,
 // 3 = byte plane + collisions resolved through the leaf-id planes after the march (production; RTO_GRID8=0 selects 1 and
@@ -145,7 +236,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
             const int idx = iy * fp.W + ix;   // full-frame pixel index: RNG offset and buffer address (volrend.cu:92-95)
             RaySetup rs;
             setup_ray(fp, ix, iy, rs);
-            float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
             WalkOut wo;
             if (rs.hit) {
                 // ctx.rng.advance(idx*SPP) (volrend.cu:157) through the row/column jump-ahead tables
@@ -193,89 +283,7 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
                     for (int s = (int)wo.steps; s < tr.max_seq; ++s) tr.leaf_seq[(size_t)idx * tr.max_seq + s] = -1;
             }
 
-            if (sh_nums > 0) {
-                // accumulate colour (rt_core.cuh:277-331)
-                const int bd = a.tree.basis_dim;
-                const __half* __restrict__ sh = a.tree.sh;
-                const int stride = a.tree.sh_stride;
-                if (bd == 9) {
-                    float b[9];
-                    sh_basis(9, rs.vdir, b);
-                    for (int i = 0; i < (int)sh_nums; ++i) {
-                        const uint4* q = reinterpret_cast<const uint4*>(sh + (size_t)mem.hit_leaf(i) * stride);
-                        const float c_i = mem.hit_cnt(i);
-                        uint32_t w[16];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint4 v = __ldg(q + k);
-                            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-                        }
-#define HV(k) f_half_bits_to_float((w[(k) >> 1] >> (((k) & 1) * 16)) & 0xffffu)
-                        float rgb[3];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-#define MB(k) (b[k] * HV(9 * c + (k)))
-                            float tmp = b[0] * HV(9 * c);
-                            tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
-                            tmp += MB(1) + MB(2) + MB(3);
-#undef MB
-                            rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
-                        }
-#undef HV
-                        out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
-                        out3 += c_i;
-                    }
-                } else if (bd > 0) {
-                    float b[25];
-#pragma unroll
-                    for (int k = 0; k < 25; ++k) b[k] = 0.f;
-                    sh_basis(bd, rs.vdir, b);
-                    for (int i = 0; i < (int)sh_nums; ++i) {
-                        const float c_i = mem.hit_cnt(i);
-                        const __half* h = sh + (size_t)mem.hit_leaf(i) * stride;
-                        float rgb[3];
-                        for (int c = 0; c < 3; ++c) {
-                            const __half* hc = h + bd * c;
-#define MB(k) (b[k] * __half2float(__ldg(hc + (k))))
-                            float tmp = b[0] * __half2float(__ldg(hc));
-                            if (bd >= 25) tmp += MB(16) + MB(17) + MB(18) + MB(19) + MB(20) + MB(21) + MB(22) + MB(23) + MB(24);
-                            if (bd >= 16) tmp += MB(9) + MB(10) + MB(11) + MB(12) + MB(13) + MB(14) + MB(15);
-                            if (bd >= 9) tmp += MB(4) + MB(5) + MB(6) + MB(7) + MB(8);
-                            if (bd >= 4) tmp += MB(1) + MB(2) + MB(3);
-#undef MB
-                            rgb[c] = f_div(c_i, 1.f + f_exp(-tmp));
-                        }
-                        out0 += rgb[0]; out1 += rgb[1]; out2 += rgb[2];
-                        out3 += c_i;
-                    }
-                } else {  // RGBA leaves (rt_core.cuh:322-326)
-                    for (int i = 0; i < (int)sh_nums; ++i) {
-                        const float c_i = mem.hit_cnt(i);
-                        const __half* h = sh + (size_t)mem.hit_leaf(i) * stride;
-                        out0 += __half2float(__ldg(h + 0)) * c_i;
-                        out1 += __half2float(__ldg(h + 1)) * c_i;
-                        out2 += __half2float(__ldg(h + 2)) * c_i;
-                        out3 += c_i;
-                    }
-                }
-                constexpr float INV_SPP = 1.0f / SPP;
-                out0 = f_mul(out0, INV_SPP); out1 = f_mul(out1, INV_SPP); out2 = f_mul(out2, INV_SPP); out3 = f_mul(out3, INV_SPP);
-            }
-
-            // background composite, offscreen branch (volrend.cu:174-179)
-            const float remain = f_mul(f_sub(1.f, out3), fp.background);
-            out0 = f_add(out0, remain); out1 = f_add(out1, remain); out2 = f_add(out2, remain);
-
-            // aux [8][H][W] (volrend.cu:187-202) and image [H][W][4] (volrend.cu:205-212)
-            if (a.aux) {
-                const size_t SIZE = (size_t)fp.W * fp.H;
-                float* q = a.aux + idx;
-                RTO_ST(q, out0); RTO_ST(q + SIZE, out1); RTO_ST(q + 2 * SIZE, out2); RTO_ST(q + 3 * SIZE, out3);
-                RTO_ST(q + 4 * SIZE, f_mul(out0, out0)); RTO_ST(q + 5 * SIZE, f_mul(out1, out1));
-                RTO_ST(q + 6 * SIZE, f_mul(out2, out2)); RTO_ST(q + 7 * SIZE, f_mul(out3, out3));
-            }
-            if (a.img) RTO_ST(a.img + idx, make_float4(out0, out1, out2, 1.0f));
-            if (a.img8) RTO_ST(a.img8 + idx, rgba8_of(out0, out1, out2, 1.0f));
+            shade_composite_write<SPP>(a, mem, rs.vdir, idx, sh_nums);
         }
         __syncwarp();
 #ifdef RTO_TILE_LOG
@@ -308,6 +316,237 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// LATENCY MODE: render_kernel_split.  Same rays, same per-ray arithmetic, same outputs as render_kernel<SPP,false,3>; what
+// changes is WHICH warp marches a ray once the kernel starts to drain.
+//
+// A frame's heaviest rays (grazing the surface through hundreds of finest-level cells) are claimed in the first
+// microseconds, and the kernel lasts until they finish: measured on the bench frame (tools/tile_log.py) the tile queue is
+// empty after 40 % of the kernel time, the remaining 60 % is a tail in which ever fewer warps march ~28 rays in lock step at
+// ~400 ns per step — every step waits for the slowest of 28 lanes' two dependent loads — while thousands of resident warp
+// slots idle.  Narrow warps step up to twice as fast (same diagnostic, 2..8 active lanes).  So: a warp that finds the tile
+// queue empty does not exit; it announces itself as WAITING.  Every 16 steps a marching warp looks at the waiting count and,
+// if somebody waits, hands the upper half of its live rays (registers + per-ray scratch, ~160 B each) over through a global
+// ring and carries on with the rest; the taker marches them (and may split again), shades them and writes their pixels.
+// The drain phase thus runs on progressively narrower warps spread over the whole GPU.  Halving stops at one ray per warp.
+// Throughput mode (several frames in flight) keeps render_kernel: there the tail is filled by the next frame's work and
+// narrow warps would only cost issue slots.
+template <int SPP>
+struct LaneRay {
+    RaySetup rs;
+    MarchState m;
+    int idx;
+    bool have;       // this lane owns a ray whose pixel it must produce
+    bool marching;   // ... and that ray is still inside the marching loop
+};
+
+__device__ __forceinline__ uint4 ld_volatile_v4(const unsigned* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int SPP>
+__device__ __forceinline__ void split_write_record(uint32_t* __restrict__ w, const LaneRay<SPP>& L, SmemRay<SPP>& mem) {
+    w[0] = (uint32_t)L.idx; w[1] = u_bits(L.m.t);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        w[2 + k] = u_bits(L.rs.dir[k]); w[5 + k] = u_bits(L.rs.cen[k]); w[8 + k] = u_bits(L.rs.invdir[k]); w[12 + k] = u_bits(L.rs.vdir[k]);
+    }
+    w[11] = u_bits(L.rs.tmax);
+    w[15] = u_bits(mem.scratch(1)); w[16] = u_bits(mem.scratch(0));
+    w[17] = L.m.nspp; w[18] = L.m.n_hits; w[19] = L.m.steps;
+#pragma unroll
+    for (int i = 0; i <= SPP; ++i) w[20 + i] = u_bits(mem.dst(i));
+#pragma unroll
+    for (int i = 0; i < SPP; ++i) { w[21 + SPP + i] = mem.hit_leaf(i); w[21 + 2 * SPP + i] = u_bits(mem.hit_cnt(i)); }
+}
+template <int SPP>
+__device__ __forceinline__ void split_read_record(const uint32_t* __restrict__ w, LaneRay<SPP>& L, SmemRay<SPP>& mem) {
+    L.idx = (int)w[0]; L.m.t = f_bits(w[1]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        L.rs.dir[k] = f_bits(w[2 + k]); L.rs.cen[k] = f_bits(w[5 + k]); L.rs.invdir[k] = f_bits(w[8 + k]); L.rs.vdir[k] = f_bits(w[12 + k]);
+        L.rs.addk[k] = L.rs.invdir[k] > 0.f ? L.rs.invdir[k] : 0.f;
+    }
+    L.rs.tmax = f_bits(w[11]);
+    L.rs.delta_scale = f_bits(w[15]);
+    L.rs.hit = true;
+    mem.scratch(1) = f_bits(w[15]); mem.scratch(0) = f_bits(w[16]);
+    L.m.nspp = w[17]; L.m.n_hits = w[18]; L.m.steps = w[19]; L.m.term = -1; L.m.bad = false;
+#pragma unroll
+    for (int i = 0; i <= SPP; ++i) mem.dst(i) = f_bits(w[20 + i]);
+#pragma unroll
+    for (int i = 0; i < SPP; ++i) { mem.hit_leaf(i) = w[21 + SPP + i]; mem.hit_cnt(i) = f_bits(w[21 + 2 * SPP + i]); }
+}
+
+// march the warp's rays to the end, handing half of the live ones to a waiting warp whenever there is one
+template <int SPP>
+__device__ __forceinline__ void split_march(const RenderArgs& a, SplitQueue* __restrict__ q, SmemRay<SPP>& mem, LaneRay<SPP>& L, int lane) {
+    static_assert(20 + 3 * SPP + 1 <= kSplitRecWords, "ray record too small for this SPP");
+    const MarchConst mc = march_const(L.rs, a.fp.sigma_thresh);
+    const float step_size = a.fp.step_size;
+    WalkOut wo;           // counters of the trace builds: unused here
+    wo.n_loads = 0;
+    auto sink = [](uint32_t, uint32_t) {};
+    for (;;) {
+        if (L.marching) {
+            const float tmax = L.rs.tmax;
+#pragma unroll 1
+            for (int k = 0; k < 16; ++k) {
+                if (!(L.m.t < tmax)) { L.marching = false; break; }
+                if (!grid_step<SPP, false, true, true>(a.tree.nodes, a.tree.grid, mem, L.rs, mc.addk, mc.sth, step_size, L.m, wo, sink)) {
+                    L.marching = false;
+                    break;
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned act = __ballot_sync(0xffffffffu, L.marching);
+        if (!act) break;
+        const int n_act = __popc(act);
+        if (n_act < 2) continue;
+        int w = 0;
+        if (lane == 0) w = *reinterpret_cast<volatile int*>(&q->waiting);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w <= 0) continue;
+        int ok = 0;
+        if (lane == 0) {   // claim one waiting warp
+            if (atomicSub(&q->waiting, 1) > 0) ok = 1;
+            else atomicAdd(&q->waiting, 1);
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+        const int k = n_act >> 1;                                   // rays handed over: the upper half in lane order
+        const int rank = __popc(act & ((1u << lane) - 1u));
+        const bool give = L.marching && rank >= n_act - k;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&q->reserve, (unsigned)k);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (give) {
+            split_write_record<SPP>(q->pool + (size_t)((base + (unsigned)(rank - (n_act - k))) & (kSplitPoolRing - 1)) * kSplitRecWords, L, mem);
+            L.marching = false;
+            L.have = false;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned slot = atomicAdd(&q->bq_tail, 1u);
+            atomicExch(&q->bq[slot & (kSplitBatchRing - 1)], 0x80000000u | ((base & (kSplitPoolRing - 1)) << 4) | (unsigned)(k - 1));
+        }
+    }
+}
+
+// resolve / shade / write the rays this warp still owns; returns how many pixels it produced (warp-uniform)
+template <int SPP>
+__device__ __forceinline__ int split_finish(const RenderArgs& a, SmemRay<SPP>& mem, LaneRay<SPP>& L) {
+    if (L.have) {
+        const uint32_t sh_nums = L.rs.hit ? L.m.n_hits : 0u;
+        resolve_hits<SPP>(a.tree.grid, mem, sh_nums);
+        shade_composite_write<SPP>(a, mem, L.rs.vdir, L.idx, sh_nums);
+    }
+    return __popc(__ballot_sync(0xffffffffu, L.have));
+}
+
+template <int SPP>
+__global__ void __launch_bounds__(kBlockThreads, 8 * 4 / kBlockWarps) render_kernel_split(const __grid_constant__ RenderArgs a) {
+    extern __shared__ uint32_t ray_smem[];
+    __shared__ unsigned s_state;
+    const int lane = threadIdx.x & 31;
+    const FrameParams& fp = a.fp;
+    const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
+    const int supers_x = (rw + kSuperX * kTileW - 1) / (kSuperX * kTileW), supers_y = (rh + kSuperY * kTileH - 1) / (kSuperY * kTileH);
+    const int n_supers = supers_x * supers_y;
+    const unsigned total = (unsigned)rw * (unsigned)rh;
+    SplitQueue* __restrict__ q = a.split;
+    SmemRay<SPP> mem{ray_smem + threadIdx.x, 0};
+    if (threadIdx.x == 0) s_state = ((unsigned)atomicAdd(a.tile_counter, 1) << 8);
+    __syncthreads();
+    LaneRay<SPP> L;
+
+    // ---- phase 1: tiles from the queue, exactly like render_kernel
+    for (;;) {
+        int sid, sub;
+        next_tile(&s_state, a.tile_counter, lane, sid, sub);
+        if (sid >= n_supers) break;
+        const int sr = sid / supers_x, sc = sid - sr * supers_x;
+        const int mid = supers_y >> 1;
+        const int srow = (sr & 1) ? mid - 1 - (sr >> 1) : mid + (sr >> 1);
+        const int tc = sc * kSuperX + (sub % kSuperX), row = srow * kSuperY + (sub / kSuperX);
+        const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
+        const int iy = a.y0 + row * kTileH + (lane / kTileW);
+        L.have = ix < a.x1 && iy < a.y1 && lane < kTileW * kTileH;
+        L.marching = false;
+        L.m = MarchState{0.f, 0u, 0u, 0u, -1, false};
+        if (L.have) {
+            L.idx = iy * fp.W + ix;
+            setup_ray(fp, ix, iy, L.rs);
+            if (L.rs.hit) {
+                const AdvanceMap rm = a.adv_rows[iy], cm = a.adv_cols[ix];
+                Pcg32 rng{cm.mult * (rm.mult * a.rng_state + rm.plus) + cm.plus, a.rng_inc};
+                sorted_thresholds_from<SPP>(rng, mem);
+                mem.scratch(0) = 0.f;
+                mem.scratch(1) = L.rs.delta_scale;
+                L.m.t = L.rs.tmin;
+                L.marching = true;
+            }
+        }
+        split_march<SPP>(a, q, mem, L, lane);
+        const int n = split_finish<SPP>(a, mem, L);
+        if (lane == 0 && n) atomicAdd(&q->done, (unsigned)n);
+        __syncwarp();
+    }
+
+    // ---- phase 2: the tile queue is empty.  Wait for rays other warps hand over, until every pixel of the frame is written.
+    if (lane == 0) atomicAdd(&q->waiting, 1);
+    for (;;) {
+        unsigned desc = 0u;
+        if (lane == 0) {
+            unsigned ns = 128;
+            for (;;) {
+                const uint4 s4 = ld_volatile_v4(&q->bq_head);   // {bq_head, bq_tail, done, reserve}
+                if ((int)(s4.y - s4.x) > 0) {
+                    if (atomicCAS(&q->bq_head, s4.x, s4.x + 1u) == s4.x) {
+                        volatile unsigned* e = &q->bq[s4.x & (kSplitBatchRing - 1)];
+                        while ((desc = *e) == 0u) {}             // published after the tail moved: a few cycles at most
+                        *e = 0u;
+                        break;
+                    }
+                    continue;
+                }
+                if (s4.z >= total) break;                        // every pixel written: the frame is complete
+                __nanosleep(ns);
+                if (ns < 2048) ns <<= 1;
+            }
+        }
+        desc = __shfl_sync(0xffffffffu, desc, 0);
+        if (!desc) break;
+        __threadfence();
+        const int k = (int)(desc & 15u) + 1;
+        const unsigned base = (desc >> 4) & (kSplitPoolRing - 1);
+        L.have = L.marching = lane < k;
+        if (L.have) split_read_record<SPP>(q->pool + (size_t)((base + (unsigned)lane) & (kSplitPoolRing - 1)) * kSplitRecWords, L, mem);
+        split_march<SPP>(a, q, mem, L, lane);
+        const int n = split_finish<SPP>(a, mem, L);
+        if (lane == 0) {
+            if (n) atomicAdd(&q->done, (unsigned)n);
+            atomicAdd(&q->waiting, 1);
+        }
+        __syncwarp();
+    }
+
+    // the last warp to leave re-arms every counter for the next launch on this context
+    if (lane == 0) {
+        const int total_warps = gridDim.x * (kBlockThreads / 32);
+        if (atomicAdd(a.tile_counter + 1, 1) == total_warps - 1) {
+            a.tile_counter[0] = 0;
+            a.tile_counter[1] = 0;
+            q->bq_head = 0; q->bq_tail = 0; q->done = 0; q->reserve = 0; q->waiting = 0;
+            __threadfence();
+        }
+    }
+}
+
 // Resident blocks per SM of the persistent kernel.  More warps raise issue utilisation but every warp then advances
 // more slowly, and the frame time is bounded below by the LONGEST ray's serial chain, so the optimum
 // is well below the occupancy limit.  RTO_RENDER_BLOCKS_PER_SM overrides the default for tuning.
@@ -321,6 +560,12 @@ static int tuned_blocks_per_sm(int occ_limit) {
 }
 
 template <int SPP>
+static auto split_kernel_ptr() -> void (*)(RenderArgs) {
+    if constexpr (SPP <= 8) return render_kernel_split<SPP>;
+    else return nullptr;
+}
+
+template <int SPP>
 static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t stream) {   // trace: 0 off, 1 tree walker, 2 production marcher
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
@@ -329,7 +574,7 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     const bool grid8 = grid_path && !(g8 && g8[0] == '0') && a.tree.grid.bricks8 != nullptr;
     const char* dh = getenv("RTO_DEFER_HITS");
     const bool defer = grid8 && !(dh && dh[0] == '0') && a.tree.grid.leaf_top != nullptr;
-    const int v = (trace ? 4 : 0) + (grid_path ? (grid8 ? (defer ? 3 : 2) : 1) : 0);
+    const int v = (SPP <= 8 && defer && !trace && a.split != nullptr) ? 8 : (trace ? 4 : 0) + (grid_path ? (grid8 ? (defer ? 3 : 2) : 1) : 0);
     const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
     // Function attributes, occupancy and the L2 set-aside are per DEVICE, so the cached launch state is indexed by the
     // current device; the one-time set-up of a slot runs under that slot's mutex (several host threads may drive the same
@@ -337,8 +582,8 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     struct DevState {
         std::mutex mu;
         int num_sms = 0;
-        size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        int occ_limit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        size_t smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int occ_limit[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         int persist = -1, max_win = 0, max_persist = 0;
         size_t persist_set = 0;   // current cudaLimitPersistingL2CacheSize this library asked for on the device
     };
@@ -347,7 +592,9 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevState& ds = dev_state[dev >= 0 && dev < kMaxDevices ? dev : 0];
+    const bool split = SPP <= 8 && defer && !trace && a.split != nullptr;
     void (*kern)(RenderArgs) =
+        split ? split_kernel_ptr<SPP>() :
         trace ? (defer ? render_kernel<SPP, true, 3> : grid8 ? render_kernel<SPP, true, 2> : grid_path ? render_kernel<SPP, true, 1> : render_kernel<SPP, true, 0>)
               : (defer ? render_kernel<SPP, false, 3> : grid8 ? render_kernel<SPP, false, 2> : grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>);
     std::unique_lock<std::mutex> lock(ds.mu);
@@ -360,7 +607,7 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
         ds.smem_set[v] = smem;
     }
     const int n_supers = ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
-    int grid = ds.num_sms * tuned_blocks_per_sm(ds.occ_limit[v]);
+    int grid = ds.num_sms * (split ? ds.occ_limit[v] : tuned_blocks_per_sm(ds.occ_limit[v]));
     const int need = n_supers;
     if (grid > need) grid = need;
     // L2 persistence window over the brick array (RTO_L2_PERSIST=0 turns it off): keeps as much of the grid as the

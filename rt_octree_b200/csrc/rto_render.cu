@@ -340,12 +340,6 @@ struct LaneRay {
     bool marching;   // ... and that ray is still inside the marching loop
 };
 
-__device__ __forceinline__ uint4 ld_volatile_v4(const unsigned* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
 template <int SPP>
 __device__ __forceinline__ void split_write_record(uint32_t* __restrict__ w, const LaneRay<SPP>& L, SmemRay<SPP>& mem) {
     w[0] = (uint32_t)L.idx; w[1] = u_bits(L.m.t);
@@ -361,8 +355,18 @@ __device__ __forceinline__ void split_write_record(uint32_t* __restrict__ w, con
 #pragma unroll
     for (int i = 0; i < SPP; ++i) { w[21 + SPP + i] = mem.hit_leaf(i); w[21 + 2 * SPP + i] = u_bits(mem.hit_cnt(i)); }
 }
+// (records are read with ld.global.cg: the same pool slot is reused by later hand-offs and L1 is not coherent)
 template <int SPP>
-__device__ __forceinline__ void split_read_record(const uint32_t* __restrict__ w, LaneRay<SPP>& L, SmemRay<SPP>& mem) {
+__device__ __forceinline__ void split_read_record(const uint32_t* wp, LaneRay<SPP>& L, SmemRay<SPP>& mem) {
+    uint32_t w[kSplitRecWords];
+    {
+        const uint4* q4 = reinterpret_cast<const uint4*>(wp);
+#pragma unroll
+        for (int i = 0; i < (20 + 3 * SPP + 1 + 3) / 4; ++i) {
+            const uint4 v = __ldcg(q4 + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    }
     L.idx = (int)w[0]; L.m.t = f_bits(w[1]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -380,16 +384,38 @@ __device__ __forceinline__ void split_read_record(const uint32_t* __restrict__ w
     for (int i = 0; i < SPP; ++i) { mem.hit_leaf(i) = w[21 + SPP + i]; mem.hit_cnt(i) = f_bits(w[21 + 2 * SPP + i]); }
 }
 
-// march the warp's rays to the end, handing half of the live ones to a waiting warp whenever there is one
+__device__ __forceinline__ uint2 ld_volatile_v2(const unsigned* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// march the warp's rays to the end, handing up to half of the live ones to a waiting warp whenever there is one.
+// Hand-off protocol (no lock, no shared line that waiting warps poll):
+//   idle warp    slot = wq_tail++ ; wq[slot] = (gen, id) ; then polls ITS OWN mailbox word mail[id]
+//   donor        every 16 steps: {head, tail} read one block of steps EARLIER (latency hidden); if somebody waits, a fresh read
+//                and CAS(wq_head, h, h+1) claim the waiter at slot h; records -> pool[id][0..k) ; fence ; mail[id] = (gen, k)
+//   last pixel   the warp whose `done` update completes the frame sets `finished` and sends kSplitTerminate to every
+//                registered waiter; a warp that registers later sees `finished` right after registering
 template <int SPP>
 __device__ __forceinline__ void split_march(const RenderArgs& a, SplitQueue* __restrict__ q, SmemRay<SPP>& mem, LaneRay<SPP>& L, int lane) {
     static_assert(20 + 3 * SPP + 1 <= kSplitRecWords, "ray record too small for this SPP");
     const MarchConst mc = march_const(L.rs, a.fp.sigma_thresh);
     const float step_size = a.fp.step_size;
+    const unsigned long long gen = (unsigned long long)a.split_gen << 32;
+    const unsigned grp = blockIdx.x % (unsigned)kSplitGroups;
+    SplitList* __restrict__ ql = &q->list[grp];
+    unsigned long long* __restrict__ ring = q->wq + (size_t)grp * kSplitWaitRing;
     WalkOut wo;           // counters of the trace builds: unused here
     wo.n_loads = 0;
     auto sink = [](uint32_t, uint32_t) {};
     for (;;) {
+        const uint2 ht = ld_volatile_v2(&ql->head);   // consumed after the block of steps below
         if (L.marching) {
             const float tmax = L.rs.tmax;
 #pragma unroll 1
@@ -405,47 +431,56 @@ __device__ __forceinline__ void split_march(const RenderArgs& a, SplitQueue* __r
         const unsigned act = __ballot_sync(0xffffffffu, L.marching);
         if (!act) break;
         const int n_act = __popc(act);
-        if (n_act < 2) continue;
-        int w = 0;
-        if (lane == 0) w = *reinterpret_cast<volatile int*>(&q->waiting);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w <= 0) continue;
-        int ok = 0;
-        if (lane == 0) {   // claim one waiting warp
-            if (atomicSub(&q->waiting, 1) > 0) ok = 1;
-            else atomicAdd(&q->waiting, 1);
+        const int stale = __shfl_sync(0xffffffffu, (int)(ht.y - ht.x), 0);
+        if (n_act < 2 || stale <= 0 || (a.split_flags & 1u)) continue;
+        unsigned id = 0u;   // waiter's warp id + 1
+        if (lane == 0) {
+            const uint2 now = ld_volatile_v2(&ql->head);
+            if ((int)(now.y - now.x) > 0 && atomicCAS(&ql->head, now.x, now.x + 1u) == now.x) {
+                unsigned long long* e = &ring[now.x & (kSplitWaitRing - 1)];
+                unsigned long long v;
+                while (((v = ld_volatile_u64(e)) >> 32) != (gen >> 32)) {}   // registered a moment ago: being written
+                id = (unsigned)v;
+                __stcg(e, 0ull);   // consumed: the ring slot must not look registered when the list wraps around
+            }
         }
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) continue;
-        const int k = n_act >> 1;                                   // rays handed over: the upper half in lane order
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (!id) continue;
+        const int k = min(n_act >> 1, kSplitMaxGive);                // rays handed over: the last k live ones in lane order
         const int rank = __popc(act & ((1u << lane) - 1u));
-        const bool give = L.marching && rank >= n_act - k;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&q->reserve, (unsigned)k);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (give) {
-            split_write_record<SPP>(q->pool + (size_t)((base + (unsigned)(rank - (n_act - k))) & (kSplitPoolRing - 1)) * kSplitRecWords, L, mem);
+        if (L.marching && rank >= n_act - k) {
+            split_write_record<SPP>(q->pool + ((size_t)(id - 1u) * kSplitMaxGive + (size_t)(rank - (n_act - k))) * kSplitRecWords, L, mem);
             L.marching = false;
             L.have = false;
         }
         __threadfence();
         __syncwarp();
-        if (lane == 0) {
-            const unsigned slot = atomicAdd(&q->bq_tail, 1u);
-            atomicExch(&q->bq[slot & (kSplitBatchRing - 1)], 0x80000000u | ((base & (kSplitPoolRing - 1)) << 4) | (unsigned)(k - 1));
-        }
+        if (lane == 0) atomicExch(&q->mail[id - 1u], gen | (unsigned long long)k);
     }
 }
 
-// resolve / shade / write the rays this warp still owns; returns how many pixels it produced (warp-uniform)
+// resolve / shade / write the rays this warp still owns, and account for them; the warp that completes the frame wakes
+// every waiting warp up
 template <int SPP>
-__device__ __forceinline__ int split_finish(const RenderArgs& a, SmemRay<SPP>& mem, LaneRay<SPP>& L) {
+__device__ __forceinline__ void split_finish(const RenderArgs& a, SplitQueue* __restrict__ q, SmemRay<SPP>& mem, LaneRay<SPP>& L, int lane,
+                                             unsigned total) {
     if (L.have) {
         const uint32_t sh_nums = L.rs.hit ? L.m.n_hits : 0u;
         resolve_hits<SPP>(a.tree.grid, mem, sh_nums);
         shade_composite_write<SPP>(a, mem, L.rs.vdir, L.idx, sh_nums);
     }
-    return __popc(__ballot_sync(0xffffffffu, L.have));
+    const unsigned n = (unsigned)__popc(__ballot_sync(0xffffffffu, L.have));
+    if (!n) return;
+    unsigned last = 0u;
+    if (lane == 0) {
+        __threadfence();
+        last = (atomicAdd(&q->done, n) + n == total) ? 1u : 0u;
+    }
+    if (!__shfl_sync(0xffffffffu, last, 0)) return;
+    // the frame is complete: no ray is alive any more, hence no donor; tell the waiters (they poll their list's flag)
+    __threadfence();
+    for (int g = lane; g < kSplitGroups; g += 32) atomicExch(&q->list[g].finished, 1u);
+    __syncwarp();
 }
 
 template <int SPP>
@@ -492,46 +527,36 @@ __global__ void __launch_bounds__(kBlockThreads, 8 * 4 / kBlockWarps) render_ker
             }
         }
         split_march<SPP>(a, q, mem, L, lane);
-        const int n = split_finish<SPP>(a, mem, L);
-        if (lane == 0 && n) atomicAdd(&q->done, (unsigned)n);
+        split_finish<SPP>(a, q, mem, L, lane, total);
         __syncwarp();
     }
 
     // ---- phase 2: the tile queue is empty.  Wait for rays other warps hand over, until every pixel of the frame is written.
-    if (lane == 0) atomicAdd(&q->waiting, 1);
-    for (;;) {
-        unsigned desc = 0u;
+    const unsigned me = blockIdx.x * (unsigned)kBlockWarps + (threadIdx.x >> 5);
+    const unsigned long long gen = (unsigned long long)a.split_gen << 32;
+    const unsigned grp = blockIdx.x % (unsigned)kSplitGroups;
+    while (me < (unsigned)q->max_warps) {
+        unsigned k = 0u;
         if (lane == 0) {
-            unsigned ns = 128;
+            const unsigned slot = atomicAdd(&q->list[grp].tail, 1u);
+            atomicExch(&q->wq[(size_t)grp * kSplitWaitRing + (slot & (kSplitWaitRing - 1))], gen | (unsigned long long)(me + 1u));
+            __threadfence();
+            unsigned ns = 32;
             for (;;) {
-                const uint4 s4 = ld_volatile_v4(&q->bq_head);   // {bq_head, bq_tail, done, reserve}
-                if ((int)(s4.y - s4.x) > 0) {
-                    if (atomicCAS(&q->bq_head, s4.x, s4.x + 1u) == s4.x) {
-                        volatile unsigned* e = &q->bq[s4.x & (kSplitBatchRing - 1)];
-                        while ((desc = *e) == 0u) {}             // published after the tail moved: a few cycles at most
-                        *e = 0u;
-                        break;
-                    }
-                    continue;
-                }
-                if (s4.z >= total) break;                        // every pixel written: the frame is complete
+                const unsigned long long v = ld_volatile_u64(&q->mail[me]);
+                if ((v >> 32) == (gen >> 32)) { k = (unsigned)v; q->mail[me] = 0ull; break; }
+                if (*reinterpret_cast<volatile unsigned*>(&q->list[grp].finished)) { k = kSplitTerminate; break; }
                 __nanosleep(ns);
-                if (ns < 2048) ns <<= 1;
+                if (ns < 512) ns <<= 1;
             }
         }
-        desc = __shfl_sync(0xffffffffu, desc, 0);
-        if (!desc) break;
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k == kSplitTerminate) break;
         __threadfence();
-        const int k = (int)(desc & 15u) + 1;
-        const unsigned base = (desc >> 4) & (kSplitPoolRing - 1);
-        L.have = L.marching = lane < k;
-        if (L.have) split_read_record<SPP>(q->pool + (size_t)((base + (unsigned)lane) & (kSplitPoolRing - 1)) * kSplitRecWords, L, mem);
+        L.have = L.marching = lane < (int)k;
+        if (L.have) split_read_record<SPP>(q->pool + ((size_t)me * kSplitMaxGive + (size_t)lane) * kSplitRecWords, L, mem);
         split_march<SPP>(a, q, mem, L, lane);
-        const int n = split_finish<SPP>(a, mem, L);
-        if (lane == 0) {
-            if (n) atomicAdd(&q->done, (unsigned)n);
-            atomicAdd(&q->waiting, 1);
-        }
+        split_finish<SPP>(a, q, mem, L, lane, total);
         __syncwarp();
     }
 
@@ -541,7 +566,8 @@ __global__ void __launch_bounds__(kBlockThreads, 8 * 4 / kBlockWarps) render_ker
         if (atomicAdd(a.tile_counter + 1, 1) == total_warps - 1) {
             a.tile_counter[0] = 0;
             a.tile_counter[1] = 0;
-            q->bq_head = 0; q->bq_tail = 0; q->done = 0; q->reserve = 0; q->waiting = 0;
+            for (int g = 0; g < kSplitGroups; ++g) { q->list[g].head = 0; q->list[g].tail = 0; q->list[g].finished = 0; }
+            q->done = 0;
             __threadfence();
         }
     }

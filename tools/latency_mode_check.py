@@ -40,7 +40,8 @@ for spp, den in ((6, True), (1, False), (8, True)):
         print("spp", spp, "frame", f, "identical" if ok else "DIFFERENT", flush=True)
         assert ok
     # timing, 100 frames each, serial
-    for name, c in (("throughput", a), ("latency", b)):
+    for name, c in (("throughput", a), ("latency", b), ("latency-nodonate", b)):
+        os.environ["RTO_SPLIT_NODONATE"] = "1" if name.endswith("nodonate") else "0"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for rep in range(2):
             e0.record()

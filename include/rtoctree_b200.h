@@ -147,12 +147,6 @@ int rto_context_create(rto_context** out, int width, int height);
 void rto_context_destroy(rto_context* ctx);
 float* rto_context_aux(rto_context* ctx);    /* device pointer, RenderContext::aux_buffer */
 float* rto_context_image(rto_context* ctx);  /* device pointer, float4 per pixel */
-/* Scheduling mode of rto_render on this context.  0 (default) = throughput: the persistent render kernel's warps leave as soon
- * as the tile queue is empty, making room for the next frame's kernels (pipelined callers).  1 = latency: for one frame at a
- * time (the reference's serial protocol, the single-frame tile split) idle warps stay and take over half of the rays of warps
- * that are still marching, repeatedly, so the long tail of a frame runs on narrow warps spread over the whole GPU.  Same rays,
- * same arithmetic, bit-identical buffers; applies to SPP <= 8 on trees with a brick grid, ignored otherwise. */
-int rto_context_set_latency_mode(rto_context* ctx, int on);
 /* ctx.rng: pcg32(seed) ; advance(delta) with the reference default delta = 2^32 (pcg32.h:145) */
 int rto_context_rng_seed(rto_context* ctx, uint64_t seed);
 int rto_context_rng_advance(rto_context* ctx, int64_t delta);

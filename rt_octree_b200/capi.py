@@ -67,7 +67,6 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_frame_create", "rto_frame_launch", "rto_frame_destroy",
     "rto_context_set_image_target", "rto_context_mark_image_written", "rto_peer_enable", "rto_ipc_export", "rto_ipc_open",
     "rto_ipc_close", "rto_event_create", "rto_event_record", "rto_stream_wait_event", "rto_event_destroy",
-    "rto_context_set_latency_mode",
 ]
 
 _lib = None
@@ -136,7 +135,6 @@ def load(path: str = LIB_PATH):
     L.rto_frame_launch.argtypes = [P, C.POINTER(C.c_float * 12), P]
     L.rto_frame_destroy.argtypes = [P]
     L.rto_frame_destroy.restype = None
-    L.rto_context_set_latency_mode.argtypes = [P, I]
     L.rto_context_set_image_target.argtypes = [P, P, P]
     L.rto_context_mark_image_written.argtypes = [P, I]
     L.rto_peer_enable.argtypes = [I]
@@ -457,11 +455,6 @@ class RenderContext:
         """Tile split: the kernels that produce the final image store it at these full-frame DEVICE pointers (possibly in a
         peer GPU's memory) instead of this context's own buffers; None restores them."""
         _check(load().rto_context_set_image_target(self._h, C.c_void_p(image_ptr), C.c_void_p(rgba8_ptr)))
-
-    def set_mode(self, latency: bool):
-        """True: latency mode (idle warps take over rays of marching ones while a frame drains: one frame at a time);
-        False (default): throughput mode (warps leave early, the next frame's kernels fill the GPU)."""
-        _check(load().rto_context_set_latency_mode(self._h, int(bool(latency))))
 
     def mark_image_written(self, rgba8_too=True):
         _check(load().rto_context_mark_image_written(self._h, int(bool(rgba8_too))))

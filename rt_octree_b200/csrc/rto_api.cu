@@ -58,12 +58,6 @@ struct rto_context {
     int adv_spp = 0;
     uint64_t adv_inc = 0;
     bool capturing = false;                // inside rto_frame_create's stream capture: no timer events
-    // latency mode (rto_context_set_latency_mode): hand-off queue of the drain-phase ray splitting, allocated on first use
-    bool latency_mode = false;
-    rto::SplitQueue* split_q = nullptr;
-    unsigned long long *split_wq = nullptr, *split_mail = nullptr;
-    uint32_t* split_pool = nullptr;
-    unsigned split_gen = 0;
     rto::Pcg32 rng{};
     // Timer
     bool timing = false;
@@ -326,7 +320,6 @@ int rto_context_create(rto_context** out, int W, int H) {
 void rto_context_destroy(rto_context* c) {
     if (!c) return;
     cudaFree(c->aux); cudaFree(c->img); cudaFree(c->img8); cudaFree(c->weight_map); cudaFree(c->guidance_map); cudaFree(c->tile_counter); cudaFree(c->adv);
-    cudaFree(c->split_q); cudaFree(c->split_wq); cudaFree(c->split_mail); cudaFree(c->split_pool);
     if (c->adv_host) cudaFreeHost(c->adv_host);
     if (c->adv_copied) cudaEventDestroy(c->adv_copied);
     for (int i = 0; i < 3; ++i) {
@@ -337,29 +330,6 @@ void rto_context_destroy(rto_context* c) {
 }
 float* rto_context_aux(rto_context* c) { return c ? c->aux : nullptr; }
 float* rto_context_image(rto_context* c) { return c ? reinterpret_cast<float*>(c->img) : nullptr; }
-int rto_context_set_latency_mode(rto_context* c, int on) {
-    if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
-    if (on && !c->split_q) {
-        int dev = 0, sms = 0;
-        RTO_CUDA(cudaGetDevice(&dev));
-        RTO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const int max_warps = sms * 64;   // every warp that can be resident at once
-        RTO_CUDA(cudaMalloc(&c->split_q, sizeof(rto::SplitQueue)));
-        RTO_CUDA(cudaMalloc(&c->split_wq, (size_t)rto::kSplitGroups * rto::kSplitWaitRing * sizeof(unsigned long long)));
-        RTO_CUDA(cudaMalloc(&c->split_mail, (size_t)max_warps * sizeof(unsigned long long)));
-        RTO_CUDA(cudaMalloc(&c->split_pool, (size_t)max_warps * rto::kSplitMaxGive * rto::kSplitRecWords * sizeof(uint32_t)));
-        RTO_CUDA(cudaMemset(c->split_wq, 0, (size_t)rto::kSplitGroups * rto::kSplitWaitRing * sizeof(unsigned long long)));
-        RTO_CUDA(cudaMemset(c->split_mail, 0, (size_t)max_warps * sizeof(unsigned long long)));
-        rto::SplitQueue q{};   // 8 KB of zeros + the pointers
-        q.wq = c->split_wq;
-        q.mail = c->split_mail;
-        q.pool = c->split_pool;
-        q.max_warps = max_warps;
-        RTO_CUDA(cudaMemcpy(c->split_q, &q, sizeof q, cudaMemcpyHostToDevice));
-    }
-    c->latency_mode = on != 0;
-    return RTO_OK;
-}
 int rto_context_rng_seed(rto_context* c, uint64_t seed) {
     if (!c) return fail(RTO_ERR_INVALID, "ctx is NULL");
     pcg32_seed(c->rng, seed);
@@ -465,13 +435,6 @@ static int fill_render_args(rto_context* c, const rto_tree* t, const rto_camera*
     a.tile_counter = c->tile_counter;
     a.adv_rows = c->adv;
     a.adv_cols = c->adv + c->H;
-    a.split = c->latency_mode ? c->split_q : nullptr;
-    if (a.split) {
-        if (++c->split_gen == 0) ++c->split_gen;
-        a.split_gen = c->split_gen;
-        const char* nd = getenv("RTO_SPLIT_NODONATE");   // A/B: the latency-mode kernel without any hand-off
-        a.split_flags = (nd && nd[0] == '1') ? 1u : 0u;
-    }
     // with the denoiser on, the final image comes from rto_denoise; the reference then renders into a separate
     // noisy surface whose rgb equals aux channels 0..2 (volrend.cu:188-192 vs :205-212), so nothing is lost here
     a.img = opt->denoise ? nullptr : c->out_img();

@@ -59,30 +59,6 @@ struct TraceOut {           // all optional (nullptr); indexed by the FULL-FRAME
     int max_seq;
 };
 
-// Latency mode of the render kernel (render_kernel_split, rto_render.cu): hand-off state for rays that marching warps give
-// to idle ones once the tile queue has run dry.  Device memory owned by the context.  Entries of `wq` and `mail` carry the
-// launch generation in their upper half, so nothing but the four counters has to be reset between launches.
-constexpr int kSplitGroups = 64;                 // waiting lists: warps of block b use list b % 64, so no list's counters are a hot line
-constexpr unsigned kSplitWaitRing = 1u << 10;    // ring of waiting-warp ids per list (>= resident warps of a list)
-constexpr int kSplitMaxGive = 8;                 // rays handed over per hand-off (= records per mailbox)
-constexpr int kSplitRecWords = 48;               // words per ray record (SPP <= 8: 20 + 3*SPP + 1 <= 45)
-struct SplitList {
-    unsigned head, tail;                         // waiting ids claimed by donors / registered by idle warps
-    unsigned finished;                           // copy of "the frame is complete" for the warps waiting on this list
-    unsigned pad[29];                            // one 128-byte line per list
-};
-struct SplitQueue {
-    SplitList list[kSplitGroups];
-    unsigned done;                               // pixels written so far                                          (own line)
-    unsigned pad1[31];
-    unsigned long long* wq;                      // [kSplitGroups][kSplitWaitRing]  generation << 32 | warp id + 1
-    unsigned long long* mail;                    // [max_warps]       generation << 32 | (count, or kSplitTerminate): one word per warp,
-                                                 //                   polled only by its owner: no shared hot line while waiting
-    uint32_t* pool;                              // [max_warps][kSplitMaxGive][kSplitRecWords] ray records of the pending hand-off
-    int max_warps;
-};
-constexpr unsigned kSplitTerminate = 0xffffu;
-
 struct RenderArgs {
     FrameParams fp;
     TreeDev tree;
@@ -94,9 +70,6 @@ struct RenderArgs {
     int* tile_counter;             // [2] device ints owned by the context: next tile, finished warps (self re-arming)
     const AdvanceMap* adv_rows;    // [H] pcg32 jump-ahead maps for iy*W*spp
     const AdvanceMap* adv_cols;    // [W] ... for ix*spp
-    SplitQueue* split;             // latency mode (nullptr: off): idle warps take over rays of busy ones while the kernel drains
-    unsigned split_gen;            // launch generation on this context (tags the hand-off queue entries), never 0
-    unsigned split_flags;          // bit 0: never hand rays over (A/B: the kernel's structure without the protocol)
     TraceOut tr;
 };
 

@@ -316,263 +316,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// LATENCY MODE: render_kernel_split.  Same rays, same per-ray arithmetic, same outputs as render_kernel<SPP,false,3>; what
-// changes is WHICH warp marches a ray once the kernel starts to drain.
-//
-// A frame's heaviest rays (grazing the surface through hundreds of finest-level cells) are claimed in the first
-// microseconds, and the kernel lasts until they finish: measured on the bench frame (tools/tile_log.py) the tile queue is
-// empty after 40 % of the kernel time, the remaining 60 % is a tail in which ever fewer warps march ~28 rays in lock step at
-// ~400 ns per step — every step waits for the slowest of 28 lanes' two dependent loads — while thousands of resident warp
-// slots idle.  Narrow warps step up to twice as fast (same diagnostic, 2..8 active lanes).  So: a warp that finds the tile
-// queue empty does not exit; it announces itself as WAITING.  Every 16 steps a marching warp looks at the waiting count and,
-// if somebody waits, hands the upper half of its live rays (registers + per-ray scratch, ~160 B each) over through a global
-// ring and carries on with the rest; the taker marches them (and may split again), shades them and writes their pixels.
-// The drain phase thus runs on progressively narrower warps spread over the whole GPU.  Halving stops at one ray per warp.
-// Throughput mode (several frames in flight) keeps render_kernel: there the tail is filled by the next frame's work and
-// narrow warps would only cost issue slots.
-template <int SPP>
-struct LaneRay {
-    RaySetup rs;
-    MarchState m;
-    int idx;
-    bool have;       // this lane owns a ray whose pixel it must produce
-    bool marching;   // ... and that ray is still inside the marching loop
-};
-
-template <int SPP>
-__device__ __forceinline__ void split_write_record(uint32_t* __restrict__ w, const LaneRay<SPP>& L, SmemRay<SPP>& mem) {
-    w[0] = (uint32_t)L.idx; w[1] = u_bits(L.m.t);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        w[2 + k] = u_bits(L.rs.dir[k]); w[5 + k] = u_bits(L.rs.cen[k]); w[8 + k] = u_bits(L.rs.invdir[k]); w[12 + k] = u_bits(L.rs.vdir[k]);
-    }
-    w[11] = u_bits(L.rs.tmax);
-    w[15] = u_bits(mem.scratch(1)); w[16] = u_bits(mem.scratch(0));
-    w[17] = L.m.nspp; w[18] = L.m.n_hits; w[19] = L.m.steps;
-#pragma unroll
-    for (int i = 0; i <= SPP; ++i) w[20 + i] = u_bits(mem.dst(i));
-#pragma unroll
-    for (int i = 0; i < SPP; ++i) { w[21 + SPP + i] = mem.hit_leaf(i); w[21 + 2 * SPP + i] = u_bits(mem.hit_cnt(i)); }
-}
-// (records are read with ld.global.cg: the same pool slot is reused by later hand-offs and L1 is not coherent)
-template <int SPP>
-__device__ __forceinline__ void split_read_record(const uint32_t* wp, LaneRay<SPP>& L, SmemRay<SPP>& mem) {
-    uint32_t w[kSplitRecWords];
-    {
-        const uint4* q4 = reinterpret_cast<const uint4*>(wp);
-#pragma unroll
-        for (int i = 0; i < (20 + 3 * SPP + 1 + 3) / 4; ++i) {
-            const uint4 v = __ldcg(q4 + i);
-            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-        }
-    }
-    L.idx = (int)w[0]; L.m.t = f_bits(w[1]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        L.rs.dir[k] = f_bits(w[2 + k]); L.rs.cen[k] = f_bits(w[5 + k]); L.rs.invdir[k] = f_bits(w[8 + k]); L.rs.vdir[k] = f_bits(w[12 + k]);
-        L.rs.addk[k] = L.rs.invdir[k] > 0.f ? L.rs.invdir[k] : 0.f;
-    }
-    L.rs.tmax = f_bits(w[11]);
-    L.rs.delta_scale = f_bits(w[15]);
-    L.rs.hit = true;
-    mem.scratch(1) = f_bits(w[15]); mem.scratch(0) = f_bits(w[16]);
-    L.m.nspp = w[17]; L.m.n_hits = w[18]; L.m.steps = w[19]; L.m.term = -1; L.m.bad = false;
-#pragma unroll
-    for (int i = 0; i <= SPP; ++i) mem.dst(i) = f_bits(w[20 + i]);
-#pragma unroll
-    for (int i = 0; i < SPP; ++i) { mem.hit_leaf(i) = w[21 + SPP + i]; mem.hit_cnt(i) = f_bits(w[21 + 2 * SPP + i]); }
-}
-
-__device__ __forceinline__ uint2 ld_volatile_v2(const unsigned* p) {
-    uint2 v;
-    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-
-// march the warp's rays to the end, handing up to half of the live ones to a waiting warp whenever there is one.
-// Hand-off protocol (no lock, no shared line that waiting warps poll):
-//   idle warp    slot = wq_tail++ ; wq[slot] = (gen, id) ; then polls ITS OWN mailbox word mail[id]
-//   donor        every 16 steps: {head, tail} read one block of steps EARLIER (latency hidden); if somebody waits, a fresh read
-//                and CAS(wq_head, h, h+1) claim the waiter at slot h; records -> pool[id][0..k) ; fence ; mail[id] = (gen, k)
-//   last pixel   the warp whose `done` update completes the frame sets `finished` and sends kSplitTerminate to every
-//                registered waiter; a warp that registers later sees `finished` right after registering
-template <int SPP>
-__device__ __forceinline__ void split_march(const RenderArgs& a, SplitQueue* __restrict__ q, SmemRay<SPP>& mem, LaneRay<SPP>& L, int lane) {
-    static_assert(20 + 3 * SPP + 1 <= kSplitRecWords, "ray record too small for this SPP");
-    const MarchConst mc = march_const(L.rs, a.fp.sigma_thresh);
-    const float step_size = a.fp.step_size;
-    const unsigned long long gen = (unsigned long long)a.split_gen << 32;
-    const unsigned grp = blockIdx.x % (unsigned)kSplitGroups;
-    SplitList* __restrict__ ql = &q->list[grp];
-    unsigned long long* __restrict__ ring = q->wq + (size_t)grp * kSplitWaitRing;
-    WalkOut wo;           // counters of the trace builds: unused here
-    wo.n_loads = 0;
-    auto sink = [](uint32_t, uint32_t) {};
-    for (;;) {
-        const uint2 ht = ld_volatile_v2(&ql->head);   // consumed after the block of steps below
-        if (L.marching) {
-            const float tmax = L.rs.tmax;
-#pragma unroll 1
-            for (int k = 0; k < 16; ++k) {
-                if (!(L.m.t < tmax)) { L.marching = false; break; }
-                if (!grid_step<SPP, false, true, true>(a.tree.nodes, a.tree.grid, mem, L.rs, mc.addk, mc.sth, step_size, L.m, wo, sink)) {
-                    L.marching = false;
-                    break;
-                }
-            }
-        }
-        __syncwarp();
-        const unsigned act = __ballot_sync(0xffffffffu, L.marching);
-        if (!act) break;
-        const int n_act = __popc(act);
-        const int stale = __shfl_sync(0xffffffffu, (int)(ht.y - ht.x), 0);
-        if (n_act < 2 || stale <= 0 || (a.split_flags & 1u)) continue;
-        unsigned id = 0u;   // waiter's warp id + 1
-        if (lane == 0) {
-            const uint2 now = ld_volatile_v2(&ql->head);
-            if ((int)(now.y - now.x) > 0 && atomicCAS(&ql->head, now.x, now.x + 1u) == now.x) {
-                unsigned long long* e = &ring[now.x & (kSplitWaitRing - 1)];
-                unsigned long long v;
-                while (((v = ld_volatile_u64(e)) >> 32) != (gen >> 32)) {}   // registered a moment ago: being written
-                id = (unsigned)v;
-                __stcg(e, 0ull);   // consumed: the ring slot must not look registered when the list wraps around
-            }
-        }
-        id = __shfl_sync(0xffffffffu, id, 0);
-        if (!id) continue;
-        const int k = min(n_act >> 1, kSplitMaxGive);                // rays handed over: the last k live ones in lane order
-        const int rank = __popc(act & ((1u << lane) - 1u));
-        if (L.marching && rank >= n_act - k) {
-            split_write_record<SPP>(q->pool + ((size_t)(id - 1u) * kSplitMaxGive + (size_t)(rank - (n_act - k))) * kSplitRecWords, L, mem);
-            L.marching = false;
-            L.have = false;
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicExch(&q->mail[id - 1u], gen | (unsigned long long)k);
-    }
-}
-
-// resolve / shade / write the rays this warp still owns, and account for them; the warp that completes the frame wakes
-// every waiting warp up
-template <int SPP>
-__device__ __forceinline__ void split_finish(const RenderArgs& a, SplitQueue* __restrict__ q, SmemRay<SPP>& mem, LaneRay<SPP>& L, int lane,
-                                             unsigned total) {
-    if (L.have) {
-        const uint32_t sh_nums = L.rs.hit ? L.m.n_hits : 0u;
-        resolve_hits<SPP>(a.tree.grid, mem, sh_nums);
-        shade_composite_write<SPP>(a, mem, L.rs.vdir, L.idx, sh_nums);
-    }
-    const unsigned n = (unsigned)__popc(__ballot_sync(0xffffffffu, L.have));
-    if (!n) return;
-    unsigned last = 0u;
-    if (lane == 0) {
-        __threadfence();
-        last = (atomicAdd(&q->done, n) + n == total) ? 1u : 0u;
-    }
-    if (!__shfl_sync(0xffffffffu, last, 0)) return;
-    // the frame is complete: no ray is alive any more, hence no donor; tell the waiters (they poll their list's flag)
-    __threadfence();
-    for (int g = lane; g < kSplitGroups; g += 32) atomicExch(&q->list[g].finished, 1u);
-    __syncwarp();
-}
-
-template <int SPP>
-__global__ void __launch_bounds__(kBlockThreads, 8 * 4 / kBlockWarps) render_kernel_split(const __grid_constant__ RenderArgs a) {
-    extern __shared__ uint32_t ray_smem[];
-    __shared__ unsigned s_state;
-    const int lane = threadIdx.x & 31;
-    const FrameParams& fp = a.fp;
-    const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
-    const int supers_x = (rw + kSuperX * kTileW - 1) / (kSuperX * kTileW), supers_y = (rh + kSuperY * kTileH - 1) / (kSuperY * kTileH);
-    const int n_supers = supers_x * supers_y;
-    const unsigned total = (unsigned)rw * (unsigned)rh;
-    SplitQueue* __restrict__ q = a.split;
-    SmemRay<SPP> mem{ray_smem + threadIdx.x, 0};
-    if (threadIdx.x == 0) s_state = ((unsigned)atomicAdd(a.tile_counter, 1) << 8);
-    __syncthreads();
-    LaneRay<SPP> L;
-
-    // ---- phase 1: tiles from the queue, exactly like render_kernel
-    for (;;) {
-        int sid, sub;
-        next_tile(&s_state, a.tile_counter, lane, sid, sub);
-        if (sid >= n_supers) break;
-        const int sr = sid / supers_x, sc = sid - sr * supers_x;
-        const int mid = supers_y >> 1;
-        const int srow = (sr & 1) ? mid - 1 - (sr >> 1) : mid + (sr >> 1);
-        const int tc = sc * kSuperX + (sub % kSuperX), row = srow * kSuperY + (sub / kSuperX);
-        const int ix = a.x0 + tc * kTileW + (lane & (kTileW - 1));
-        const int iy = a.y0 + row * kTileH + (lane / kTileW);
-        L.have = ix < a.x1 && iy < a.y1 && lane < kTileW * kTileH;
-        L.marching = false;
-        L.m = MarchState{0.f, 0u, 0u, 0u, -1, false};
-        if (L.have) {
-            L.idx = iy * fp.W + ix;
-            setup_ray(fp, ix, iy, L.rs);
-            if (L.rs.hit) {
-                const AdvanceMap rm = a.adv_rows[iy], cm = a.adv_cols[ix];
-                Pcg32 rng{cm.mult * (rm.mult * a.rng_state + rm.plus) + cm.plus, a.rng_inc};
-                sorted_thresholds_from<SPP>(rng, mem);
-                mem.scratch(0) = 0.f;
-                mem.scratch(1) = L.rs.delta_scale;
-                L.m.t = L.rs.tmin;
-                L.marching = true;
-            }
-        }
-        split_march<SPP>(a, q, mem, L, lane);
-        split_finish<SPP>(a, q, mem, L, lane, total);
-        __syncwarp();
-    }
-
-    // ---- phase 2: the tile queue is empty.  Wait for rays other warps hand over, until every pixel of the frame is written.
-    const unsigned me = blockIdx.x * (unsigned)kBlockWarps + (threadIdx.x >> 5);
-    const unsigned long long gen = (unsigned long long)a.split_gen << 32;
-    const unsigned grp = blockIdx.x % (unsigned)kSplitGroups;
-    while (me < (unsigned)q->max_warps) {
-        unsigned k = 0u;
-        if (lane == 0) {
-            const unsigned slot = atomicAdd(&q->list[grp].tail, 1u);
-            atomicExch(&q->wq[(size_t)grp * kSplitWaitRing + (slot & (kSplitWaitRing - 1))], gen | (unsigned long long)(me + 1u));
-            __threadfence();
-            unsigned ns = 32;
-            for (;;) {
-                const unsigned long long v = ld_volatile_u64(&q->mail[me]);
-                if ((v >> 32) == (gen >> 32)) { k = (unsigned)v; q->mail[me] = 0ull; break; }
-                if (*reinterpret_cast<volatile unsigned*>(&q->list[grp].finished)) { k = kSplitTerminate; break; }
-                __nanosleep(ns);
-                if (ns < 512) ns <<= 1;
-            }
-        }
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k == kSplitTerminate) break;
-        __threadfence();
-        L.have = L.marching = lane < (int)k;
-        if (L.have) split_read_record<SPP>(q->pool + ((size_t)me * kSplitMaxGive + (size_t)lane) * kSplitRecWords, L, mem);
-        split_march<SPP>(a, q, mem, L, lane);
-        split_finish<SPP>(a, q, mem, L, lane, total);
-        __syncwarp();
-    }
-
-    // the last warp to leave re-arms every counter for the next launch on this context
-    if (lane == 0) {
-        const int total_warps = gridDim.x * (kBlockThreads / 32);
-        if (atomicAdd(a.tile_counter + 1, 1) == total_warps - 1) {
-            a.tile_counter[0] = 0;
-            a.tile_counter[1] = 0;
-            for (int g = 0; g < kSplitGroups; ++g) { q->list[g].head = 0; q->list[g].tail = 0; q->list[g].finished = 0; }
-            q->done = 0;
-            __threadfence();
-        }
-    }
-}
-
 // Resident blocks per SM of the persistent kernel.  More warps raise issue utilisation but every warp then advances
 // more slowly, and the frame time is bounded below by the LONGEST ray's serial chain, so the optimum
 // is well below the occupancy limit.  RTO_RENDER_BLOCKS_PER_SM overrides the default for tuning.
@@ -586,12 +329,6 @@ static int tuned_blocks_per_sm(int occ_limit) {
 }
 
 template <int SPP>
-static auto split_kernel_ptr() -> void (*)(RenderArgs) {
-    if constexpr (SPP <= 8) return render_kernel_split<SPP>;
-    else return nullptr;
-}
-
-template <int SPP>
 static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t stream) {   // trace: 0 off, 1 tree walker, 2 production marcher
     const int rw = a.x1 - a.x0, rh = a.y1 - a.y0;
     if (rw <= 0 || rh <= 0) return cudaSuccess;
@@ -600,7 +337,7 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     const bool grid8 = grid_path && !(g8 && g8[0] == '0') && a.tree.grid.bricks8 != nullptr;
     const char* dh = getenv("RTO_DEFER_HITS");
     const bool defer = grid8 && !(dh && dh[0] == '0') && a.tree.grid.leaf_top != nullptr;
-    const int v = (SPP <= 8 && defer && !trace && a.split != nullptr) ? 8 : (trace ? 4 : 0) + (grid_path ? (grid8 ? (defer ? 3 : 2) : 1) : 0);
+    const int v = (trace ? 4 : 0) + (grid_path ? (grid8 ? (defer ? 3 : 2) : 1) : 0);
     const size_t smem = (size_t)SmemRay<SPP>::words(grid_path ? -1 : a.tree.max_depth) * kBlockThreads * sizeof(uint32_t);
     // Function attributes, occupancy and the L2 set-aside are per DEVICE, so the cached launch state is indexed by the
     // current device; the one-time set-up of a slot runs under that slot's mutex (several host threads may drive the same
@@ -608,8 +345,8 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     struct DevState {
         std::mutex mu;
         int num_sms = 0;
-        size_t smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        int occ_limit[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int occ_limit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int persist = -1, max_win = 0, max_persist = 0;
         size_t persist_set = 0;   // current cudaLimitPersistingL2CacheSize this library asked for on the device
     };
@@ -618,9 +355,7 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevState& ds = dev_state[dev >= 0 && dev < kMaxDevices ? dev : 0];
-    const bool split = SPP <= 8 && defer && !trace && a.split != nullptr;
     void (*kern)(RenderArgs) =
-        split ? split_kernel_ptr<SPP>() :
         trace ? (defer ? render_kernel<SPP, true, 3> : grid8 ? render_kernel<SPP, true, 2> : grid_path ? render_kernel<SPP, true, 1> : render_kernel<SPP, true, 0>)
               : (defer ? render_kernel<SPP, false, 3> : grid8 ? render_kernel<SPP, false, 2> : grid_path ? render_kernel<SPP, false, 1> : render_kernel<SPP, false, 0>);
     std::unique_lock<std::mutex> lock(ds.mu);
@@ -633,7 +368,7 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
         ds.smem_set[v] = smem;
     }
     const int n_supers = ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
-    int grid = ds.num_sms * (split ? ds.occ_limit[v] : tuned_blocks_per_sm(ds.occ_limit[v]));
+    int grid = ds.num_sms * tuned_blocks_per_sm(ds.occ_limit[v]);
     const int need = n_supers;
     if (grid > need) grid = need;
     // L2 persistence window over the brick array (RTO_L2_PERSIST=0 turns it off): keeps as much of the grid as the

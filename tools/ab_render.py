@@ -19,9 +19,6 @@ tree = bench.load_tree(); poses, fx = bench.workload_poses()
 spp = int(os.environ.get("AB_SPP", "6")); den = spp != 1
 rig = bench.Rig(capi, torch, tree, S.make_guidance_weights(0), bench.W, bench.H, fx, spp, den, poses, 8)
 frames = list(range(200))
-lat = os.environ.get("AB_LATENCY_MODE")
-if lat is not None and hasattr(rig.ctxs[0], "set_mode"):
-    for c in rig.ctxs: c.set_mode(int(lat))
 sp = rig.serial_protocol(frames, 0.6)
 pl = rig.pipelined(frames, 4, 10, 0.6, lambda: None)
 print(json.dumps({"render_ms": sp["render_ms"], "net_ms": sp["net_ms"], "filter_ms": sp["filter_ms"],

@@ -305,9 +305,27 @@ class Rig:
         if self.net:
             self.net.denoise(self.cam, c, stream=sp)
 
-    # ---- device-resident throughput: CUDA events around reps x K frames issued round-robin on n_pipe slots
-    def pipelined(self, my_frames, n_pipe, warm, min_s, barrier):
+    # ---- device-resident throughput: CUDA events around reps x K frames issued round-robin on n_pipe slots; every frame is
+    #      one rto_frame graph launch (render -> net -> filter, no read-back) unless graph=False (three separate launches)
+    def pipelined(self, my_frames, n_pipe, warm, min_s, barrier, graph=True):
         torch, K = self.torch, len(my_frames)
+        if graph:
+            key = ("none", n_pipe, True)
+            if key not in self.frames_cache:
+                self.frames_cache[key] = {"bufs": [], "frames": [self.capi.Frame(self.ctxs[k], self.tree, self.net, self.opt, self.cam.fx, self.cam.fy)
+                                                                  for k in range(n_pipe)]}
+            graphs = self.frames_cache[key]["frames"]
+            plain_frame = self.frame
+
+            def gframe(slot, f):
+                self.ctxs[slot].rng_set_frame(f, WARMUP_RNG)
+                graphs[slot].launch(self.poses[f % len(self.poses)], stream=self.streams[slot].cuda_stream)
+
+            self.frame = gframe
+            try:
+                return self.pipelined(my_frames, n_pipe, warm, min_s, barrier, graph=False)
+            finally:
+                self.frame = plain_frame
 
         def block(reps):
             e0 = torch.cuda.Event(enable_timing=True)
@@ -458,7 +476,7 @@ def run_cuda_arm(args):
     if rank == 0:
         clocks.start()
     t_clk0 = clocks.mark()
-    pl = rig.pipelined(my_frames, n_pipe, Wm, min_s, barrier)
+    pl = rig.pipelined(my_frames, n_pipe, Wm, min_s, barrier, graph=not args.no_graph)
     t_clk1 = clocks.mark()
     barrier()
     sp = rig.serial_protocol(my_frames, min_s)
@@ -500,7 +518,7 @@ def run_cuda_arm(args):
     if world == 1 and not args.no_extras:
         # ---- BASELINE config 2: same octree, SPP 1, denoiser off (the image comes straight out of the render kernel)
         rig2 = Rig(capi, torch, tree, weights, W, H, fx, 1, False, poses, NSLOT)
-        p2 = rig2.pipelined(my_frames, n_pipe, Wm, min_s, barrier)
+        p2 = rig2.pipelined(my_frames, n_pipe, Wm, min_s, barrier, graph=not args.no_graph)
         s2 = rig2.serial_protocol(my_frames, min_s)
         x2 = rig2.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
         b2, c2 = algorithmic_bytes(capi, rig2.tree, rig2.ctxs[0], rig2.cam, rig2.opt, poses, my_frames[: min(K, 8)], W, H)
@@ -521,7 +539,7 @@ def run_cuda_arm(args):
         Ktt = min(K, 50)
         ttf = my_frames[:Ktt]
         rig_tt = Rig(capi, torch, tt_tree, weights, TT_W, TT_H, TT_FX, SPP, True, tt_poses, max(args.pipe, 4))
-        p4 = rig_tt.pipelined(ttf, n_pipe, Wm, min_s, barrier)
+        p4 = rig_tt.pipelined(ttf, n_pipe, Wm, min_s, barrier, graph=not args.no_graph)
         s4 = rig_tt.serial_protocol(ttf, min_s)
         x4 = rig_tt.e2e(ttf, max(args.pipe, 4), "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
         b4, c4 = algorithmic_bytes(capi, rig_tt.tree, rig_tt.ctxs[0], rig_tt.cam, rig_tt.opt, tt_poses, ttf[: min(Ktt, 4)], TT_W, TT_H)
@@ -573,7 +591,8 @@ def run_cuda_arm(args):
             "dtype": "f32 traversal/shade, f16 GuidanceNet", "data": "synthetic",
             "reps": pl["reps"], "timed_region_s": pl["ms_total"] * 1e-3,
             "config": cfg,
-            "value_protocol": "%d frames in flight on %d (context, stream) pairs, device-timed over reps x steps frames" % (n_pipe, n_pipe),
+            "value_protocol": "%d frames in flight on %d (context, stream) pairs, %s, device-timed over reps x steps frames"
+                              % (n_pipe, n_pipe, "three launches per frame" if args.no_graph else "one rto_frame graph launch per frame"),
             "value_reference_protocol": fps_protocol,
             "reference_protocol": {"definition": "1000 / (render + net + filter ms): one stream, cudaEvents per stage, host sync per frame "
                                                  "(Timer::report, render_context.hpp:190-206)", "frames": sp["frames"],
@@ -628,7 +647,7 @@ def main():
     ap.add_argument("--pipe", type=int, default=4, help="frames in flight (contexts/streams) of the device-timed loop")
     ap.add_argument("--serial", action="store_true", help="one stream, frames strictly back to back, for `value` too")
     ap.add_argument("--min-seconds", type=float, default=0.5, help="minimum duration of every timed region (the K-frame block is repeated)")
-    ap.add_argument("--no-graph", action="store_true", help="e2e loops issue separate launches instead of one rto_frame graph launch")
+    ap.add_argument("--no-graph", action="store_true", help="issue separate launches instead of one rto_frame graph launch per frame")
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / reference_cuda side measurements")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (SPP 1, T&T 1080p, write_buffer, tile split)")
     ap.add_argument("--no-tt", action="store_true", help="skip BASELINE config 4 (saves the depth-10 tree generation)")

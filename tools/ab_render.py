@@ -20,9 +20,10 @@ spp = int(os.environ.get("AB_SPP", "6")); den = spp != 1
 rig = bench.Rig(capi, torch, tree, S.make_guidance_weights(0), bench.W, bench.H, fx, spp, den, poses, 8)
 frames = list(range(200))
 sp = rig.serial_protocol(frames, 0.6)
-pl = rig.pipelined(frames, 4, 10, 0.6, lambda: None)
+pl = rig.pipelined(frames, 4, 10, 0.6, lambda: None, graph=os.environ.get("AB_GRAPH", "1") == "1")
 print(json.dumps({"render_ms": sp["render_ms"], "net_ms": sp["net_ms"], "filter_ms": sp["filter_ms"],
-                  "serial_fps": 1e3 / (sp["render_ms"] + sp["net_ms"] + sp["filter_ms"]), "pipe_fps": 1e3 * pl["reps"] * 200 / pl["ms_total"]}))
+                  "serial_fps": 1e3 / (sp["render_ms"] + sp["net_ms"] + sp["filter_ms"]), "serial_wall_fps": sp["wall_fps"],
+                  "pipe_fps": 1e3 * pl["reps"] * 200 / pl["ms_total"]}))
 ''' % ROOT
 
 variants = []

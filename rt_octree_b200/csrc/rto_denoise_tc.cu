@@ -235,7 +235,6 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     {
         uint4* z = reinterpret_cast<uint4*>(smem + C::OFF_ZERO);
         if (tid < 128) z[tid] = make_uint4(0, 0, 0, 0);
-        pdl_wait_for_predecessor();   // everything above ran under the render kernel's tail; aux is complete from here on
         uint4* in = reinterpret_cast<uint4*>(smem + C::OFF_IN);
         const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0;
         if (vec) {
@@ -523,7 +522,6 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
     const int tid = threadIdx.x;
     const int bx = blockIdx.x * BW, by = y0 + blockIdx.y * BH;
     const size_t HW = (size_t)W * H;
-    pdl_wait_for_predecessor();   // the GuidanceNet kernel's maps
     const bool interior = (W & 3) == 0 && bx >= R && bx + BW + R <= W && by >= R && by + BH + R <= H &&
                           (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && (reinterpret_cast<uintptr_t>(guidance) & 15) == 0;
     if (interior) filter_pass1<false>(aux, guidance, W, H, bx, by, tid, Hs);
@@ -584,17 +582,8 @@ static cudaError_t launch_net_th(const NetDev& net, const void* packed, const De
         attr_set[dev] = true;
     }
     dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + TH - 1) / TH);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(tc::THREADS);
-    cfg.dynamicSmemBytes = tc::Cfg<TH>::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, guidance_net_tc_kernel<TH>, static_cast<const unsigned char*>(packed), d, net.fused_bias);
+    guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias);
+    return cudaGetLastError();
 }
 
 // Tile height.  Measured on B200 with four frames in flight (bench workload): TH 8 / 10 / 12 -> 4747 / 4760 / 4715 frames/s,
@@ -631,17 +620,8 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
         attr_set[dev] = true;
     }
     dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(fs::THREADS);
-    cfg.dynamicSmemBytes = fs::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, filter_sep_kernel, aux, weight, guidance, W, H, y0, y1, out, out8);
+    filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out, out8);
+    return cudaGetLastError();
 }
 
 }  // namespace rto

@@ -18,18 +18,7 @@
 #define RTO_LD_LAST(p) __ldg(p)
 #endif
 
-// Programmatic dependent launch (PDL): the three kernels of a frame (render -> GuidanceNet -> filter, and the next frame's
-// render behind them on the same stream) are launched with programmatic stream serialization, so the CTAs of kernel N+1 become
-// resident and run their prologue (TMEM allocation, barrier set-up, weight bulk copy, ...) on the SMs kernel N's tail has
-// already freed, and block in griddepcontrol.wait until kernel N has completed and flushed.  Every kernel waits BEFORE its
-// first access to a buffer the predecessor writes or reads.  RTO_PDL=0 in the environment launches them the ordinary way.
-#if defined(__CUDACC__)
-__device__ __forceinline__ void pdl_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#endif
-
 namespace rto {
-
-bool pdl_enabled();   // rto_render.cu: RTO_PDL != 0
 
 constexpr int kMaxDevices = 64;   // per-device launch state (function attributes are per device)
 

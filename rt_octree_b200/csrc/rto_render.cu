@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
     const int n_supers = supers_x * supers_y;
     SmemRay<SPP> mem{ray_smem + threadIdx.x, GRID ? 0 : a.tree.max_depth + 1};
     const uint32_t* __restrict__ nodes = a.tree.nodes;
-    pdl_wait_for_predecessor();   // the previous frame's filter still reads aux, its render re-armed the tile counter
     if (threadIdx.x == 0) s_state = ((unsigned)atomicAdd(a.tile_counter, 1) << 8);
     __syncthreads();
 
@@ -317,14 +316,6 @@ __global__ void __launch_bounds__(kBlockThreads, (TRACE ? 4 : (SPP <= 8 ? RTO_RE
     }
 }
 
-bool pdl_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("RTO_PDL");
-        return !(e && e[0] == '0');
-    }();
-    return on;
-}
-
 // Resident blocks per SM of the persistent kernel.  More warps raise issue utilisation but every warp then advances
 // more slowly, and the frame time is bounded below by the LONGEST ray's serial chain, so the optimum
 // is well below the occupancy limit.  RTO_RENDER_BLOCKS_PER_SM overrides the default for tuning.
@@ -408,31 +399,26 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
     const size_t persist_set = ds.persist_set;
     const int max_win = ds.max_win;
     lock.unlock();
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kBlockThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    unsigned n_at = 0;
     if (use_window && persist_set > 0) {
         if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
-        at[n_at].id = cudaLaunchAttributeAccessPolicyWindow;
-        at[n_at].val.accessPolicyWindow.base_ptr = grid8 ? (void*)const_cast<uint8_t*>(a.tree.grid.bricks8) : (void*)const_cast<uint32_t*>(a.tree.grid.bricks);
-        at[n_at].val.accessPolicyWindow.num_bytes = bytes;
-        at[n_at].val.accessPolicyWindow.hitRatio = bytes <= persist_set ? 1.0f : (float)persist_set / (float)bytes;
-        at[n_at].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        at[n_at].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        ++n_at;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kBlockThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[0].val.accessPolicyWindow.base_ptr = grid8 ? (void*)const_cast<uint8_t*>(a.tree.grid.bricks8) : (void*)const_cast<uint32_t*>(a.tree.grid.bricks);
+        at[0].val.accessPolicyWindow.num_bytes = bytes;
+        at[0].val.accessPolicyWindow.hitRatio = bytes <= persist_set ? 1.0f : (float)persist_set / (float)bytes;
+        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, a);
     }
-    if (pdl_enabled()) {   // see rto_internal.h: start behind the previous kernel's tail, wait inside the kernel
-        at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[n_at].val.programmaticStreamSerializationAllowed = 1;
-        ++n_at;
-    }
-    cfg.attrs = at;
-    cfg.numAttrs = n_at;
-    return cudaLaunchKernelEx(&cfg, kern, a);
+    kern<<<grid, kBlockThreads, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 #ifdef RTO_TILE_LOG

@@ -16,7 +16,7 @@
 #include "rto_tree.h"
 
 namespace rto {
-cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream);
+cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, bool exp_guidance, cudaStream_t stream);
 cudaError_t launch_filter_fast(const float* aux, const float* weight, const float* guidance, int W, int H, int y0, int y1,
                                float4* out, uchar4* out8, cudaStream_t stream);
 size_t denoise_tc_packed_bytes();
@@ -540,7 +540,8 @@ int rto_denoise_rows(rto_context* c, const rto_net* n, int y0, int y1, void* str
                         y1 + L > c->H ? c->H : y1 + L};
     const bool tc = n->impl == 0 && n->tc_capable();
     timer_start(c, 1, s);
-    cudaError_t e = tc ? rto::launch_guidance_net_tc(n->dev(), n->packed, dn, s) : rto::launch_guidance_net_simt(n->dev(), dn, s);
+    // tensor-core path: the map written for the separable filter holds e^{guidance} (exponentiated once, in the net epilogue)
+    cudaError_t e = tc ? rto::launch_guidance_net_tc(n->dev(), n->packed, dn, true, s) : rto::launch_guidance_net_simt(n->dev(), dn, s);
     timer_stop(c, 1, s);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch (%s): %s", tc ? "tcgen05" : "simt", cudaGetErrorString(e));
     timer_start(c, 2, s);
@@ -565,7 +566,7 @@ int rto_net_forward(const rto_net* n, const float* aux_dev, int W, int H, float*
     if (!n || !aux_dev || !weight_dev || !guidance_dev) return fail(RTO_ERR_INVALID, "NULL argument");
     if (W <= 0 || H <= 0) return fail(RTO_ERR_INVALID, "bad size");
     rto::DenoiseArgs d{aux_dev, nullptr, weight_dev, guidance_dev, W, H, 0, H};
-    cudaError_t e = (n->impl == 0 && n->tc_capable()) ? rto::launch_guidance_net_tc(n->dev(), n->packed, d, (cudaStream_t)stream)
+    cudaError_t e = (n->impl == 0 && n->tc_capable()) ? rto::launch_guidance_net_tc(n->dev(), n->packed, d, false, (cudaStream_t)stream)
                                                        : rto::launch_guidance_net_simt(n->dev(), d, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RTO_ERR_CUDA, "guidance net launch: %s", cudaGetErrorString(e));
     ++g_launches;

@@ -203,7 +203,7 @@ __device__ __forceinline__ uint4 pack8(float c0, float c1, float c2, float c3, f
 // The tensor pipe therefore runs conv1 of later tiles and conv2 of earlier tiles underneath both epilogues.
 template <int TH>
 __global__ void __launch_bounds__(tc::THREADS, 2)
-guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseArgs d, int fused_bias) {
+guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseArgs d, int fused_bias, int exp_guidance) {
     using namespace tc;
     using C = Cfg<TH>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -431,7 +431,9 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
                         RTO_ST(d.weight_map + l * HW + p, e[l] * inv);
-                        RTO_ST(d.guidance_map + l * HW + p, o[4 + l]);
+                        // exp_guidance: the map feeds filter_sep_kernel only, which needs E_l = e^{g_l} at every pixel of every
+                        // window: computed HERE once per pixel (the filter's threads overlap and would each redo it three times)
+                        RTO_ST(d.guidance_map + l * HW + p, exp_guidance ? __expf(o[4 + l]) : o[4 + l]);
                     }
                 }
             }
@@ -496,10 +498,8 @@ __device__ __forceinline__ void filter_pass1(const float* __restrict__ aux, cons
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const int S = l + 1;
-        float e[12];
+        float e[12];   // E_l = e^{g_l}, already exponentiated by the GuidanceNet epilogue; load12 yields 0 outside the image
         load12<GUARD>(guidance + l * HW, W, vec, rowin, rowoff, xs, e);
-#pragma unroll
-        for (int i = R - S; i <= R + 3 + S; ++i) e[i] = (!GUARD || (rowin && xs + i >= 0 && xs + i < W)) ? __expf(e[i]) : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -514,7 +514,7 @@ __device__ __forceinline__ void filter_pass1(const float* __restrict__ aux, cons
 }
 
 __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float* __restrict__ aux, const float* __restrict__ weight,
-                                                                   const float* __restrict__ guidance, int W, int H, int y0,
+                                                                   const float* __restrict__ guidance /* e^{g}: see the net epilogue */, int W, int H, int y0,
                                                                    int y1, float4* __restrict__ out, uchar4* __restrict__ out8) {
     using namespace fs;
     extern __shared__ __align__(16) unsigned char fsm[];
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 }
 
 template <int TH>
-static cudaError_t launch_net_th(const NetDev& net, const void* packed, const DenoiseArgs& d, int rows, cudaStream_t stream) {
+static cudaError_t launch_net_th(const NetDev& net, const void* packed, const DenoiseArgs& d, int rows, bool exp_guidance, cudaStream_t stream) {
     // per device: the opt-in shared-memory size is a per-device function attribute.  Atomic flags: several host threads may
     // drive the same device (volrend_headless --gpu_list 0,0); setting the attribute twice is harmless.
     static std::atomic<bool> attr_set[kMaxDevices] = {};
@@ -582,14 +582,16 @@ static cudaError_t launch_net_th(const NetDev& net, const void* packed, const De
         attr_set[dev] = true;
     }
     dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + TH - 1) / TH);
-    guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias);
+    guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias,
+                                                                                       exp_guidance ? 1 : 0);
     return cudaGetLastError();
 }
 
 // Tile height.  Measured on B200 with four frames in flight (bench workload): TH 8 / 10 / 12 -> 4747 / 4760 / 4715 frames/s,
 // TH 14 -> 4197: the kernel's own time is the same (45 us) for all of them, but at TH = 14 two CTAs take 218 KB of
 // shared memory per SM and nothing of the neighbouring frames' kernels can be co-resident.  RTO_NET_TILE_H overrides.
-cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, cudaStream_t stream) {
+// exp_guidance: write e^{guidance} instead of guidance (the form filter_sep_kernel consumes; rto_net_forward keeps guidance)
+cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const DenoiseArgs& d, bool exp_guidance, cudaStream_t stream) {
     const int rows = d.y1 - d.y0;
     if (rows <= 0) return cudaSuccess;
     static const int th = [] {   // thread-safe one-time initialisation
@@ -598,10 +600,10 @@ cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const 
         return (t == 8 || t == 10 || t == 12 || t == 14) ? t : 10;
     }();
     switch (th) {
-        case 8: return launch_net_th<8>(net, packed, d, rows, stream);
-        case 12: return launch_net_th<12>(net, packed, d, rows, stream);
-        case 14: return launch_net_th<14>(net, packed, d, rows, stream);
-        default: return launch_net_th<10>(net, packed, d, rows, stream);
+        case 8: return launch_net_th<8>(net, packed, d, rows, exp_guidance, stream);
+        case 12: return launch_net_th<12>(net, packed, d, rows, exp_guidance, stream);
+        case 14: return launch_net_th<14>(net, packed, d, rows, exp_guidance, stream);
+        default: return launch_net_th<10>(net, packed, d, rows, exp_guidance, stream);
     }
 }
 

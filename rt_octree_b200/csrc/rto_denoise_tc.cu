@@ -5,6 +5,9 @@
 // them through libtorch/cuDNN (src/denoiser/denoiser.cpp:46).  Here each CTA owns a 60 x TH pixel tile (TH = 10) and
 // runs both convolutions as implicit GEMMs with M = pixels:
 //
+//   * the fp32 input tile (+2 px halo: 64 x (TH+4) pixels x 8 planes) arrives by ONE 3-D tensor-map TMA load
+//     (cp.async.bulk.tensor.3d, hardware zero fill outside the image) into shared memory that the activation buffer reuses
+//     later, and is converted there — conflict-free — to the operand layout;
 //   * the tile (+2 px halo) is staged in shared memory PIXEL-MAJOR with a pitch of 64 pixels, 8 fp16 channels =
 //     one 16-byte row of a K-major / no-swizzle core matrix.  Because consecutive pixels are consecutive 16-byte
 //     rows, the A operand of filter tap (dy,dx) is the SAME buffer viewed through a descriptor whose start address
@@ -26,6 +29,7 @@
 // The kernel filter (denoiser/extension/filtering.cu:108-228) then runs as ONE launch for all levels, separated into
 // a horizontal and a vertical box sum of e^{g} * (r,g,b,1) (guidance is in [0,6] after relu6, so the reference's
 // max-subtraction is not needed for range).
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -62,8 +66,13 @@ struct Cfg {
     static constexpr int OFF_ZERO = OFF_W2 + 6 * 1024;                      // zero block: must lie ABOVE every operand start address
     static constexpr int OFF_BIAS = OFF_ZERO + 2048;
     static constexpr int OFF_XCH = OFF_BIAS + 40 * 4;                       // epilogue-2 neighbour exchange: [team][parity][pair][dir][8] floats
-    static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 2 * 2 * 32;            // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights
-    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES + 1);
+    static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 2 * 2 * 32;            // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights | input tile
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES + 2);
+    // fp32 input tile as the tensor-map TMA load delivers it: [8 planes][TH+4 rows][64 px].  It lives where the conv1
+    // activations go later (OFF_MID): it is consumed (converted to fp16, pixel-major) before the first MMA is issued.
+    static constexpr int OFF_STAGE = OFF_MID;
+    static constexpr int STAGE_BYTES = 8 * (TH + 4) * PW * 4;
+    static_assert(STAGE_BYTES <= 4 * MID_PX * 16 && OFF_STAGE % 128 == 0, "the fp32 staging tile fits the activation buffer, 128-byte aligned");
     static constexpr int SMEM_BYTES = OFF_TMEM + 8;
     static_assert(N1_TILES * 32 <= TMEM_COLS, "conv1 accumulators must fit the TMEM allocation");
     static_assert(TH % 2 == 0 && N2_TILES <= N1_TILES, "conv2 tiles are row pairs and reuse the TMEM columns of conv1 tile j");
@@ -132,6 +141,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 3-D tiled tensor-map load global -> shared (TMA): box = the tensor map's boxDim, coordinates in elements (may be negative or
+// past the end: out-of-bounds elements are ZERO-filled by the hardware), completion as transaction bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
@@ -203,7 +218,8 @@ __device__ __forceinline__ uint4 pack8(float c0, float c1, float c2, float c3, f
 // The tensor pipe therefore runs conv1 of later tiles and conv2 of earlier tiles underneath both epilogues.
 template <int TH>
 __global__ void __launch_bounds__(tc::THREADS, 2)
-guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseArgs d, int fused_bias, int exp_guidance) {
+guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsigned char* __restrict__ packed, const DenoiseArgs d,
+                       int fused_bias, int exp_guidance, int use_tma) {
     using namespace tc;
     using C = Cfg<TH>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -213,7 +229,7 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
     const size_t HW = (size_t)W * H;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar_c1 = s_base + C::OFF_BAR, bar_mid = bar_c1 + 8 * C::N1_TILES, bar_c2 = bar_mid + 8 * C::N1_TILES;
-    const uint32_t bar_w = bar_c2 + 8 * C::N2_TILES;
+    const uint32_t bar_w = bar_c2 + 8 * C::N2_TILES, bar_in = bar_w + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
     // ---- one-time setup: TMEM allocation (warp 0), mbarriers (one thread)
@@ -225,7 +241,12 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
         for (int i = 0; i < C::N1_TILES; ++i) { mbar_init(bar_c1 + 8 * i, 1); mbar_init(bar_mid + 8 * i, 128); }
         for (int j = 0; j < C::N2_TILES; ++j) mbar_init(bar_c2 + 8 * j, 1);
         mbar_init(bar_w, 1);
+        mbar_init(bar_in, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        if (use_tma) {   // the whole fp32 input tile: 8 planes x (TH+4) rows x 64 px starting at image (bx-2, by-2), zero outside
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_in), "n"(C::STAGE_BYTES) : "memory");
+            tma_load_3d(s_base + C::OFF_STAGE, &aux_map, bx - 2, by - 2, 0, bar_in);
+        }
         // packed weights + biases: two bulk async copies (TMA engine, no registers, no thread instructions) signalling bar_w
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_w), "n"(PK_BYTES) : "memory");
         bulk_g2s(s_base + C::OFF_W1, packed, PK_BIAS, bar_w);
@@ -237,7 +258,18 @@ guidance_net_tc_kernel(const unsigned char* __restrict__ packed, const DenoiseAr
         if (tid < 128) z[tid] = make_uint4(0, 0, 0, 0);
         uint4* in = reinterpret_cast<uint4*>(smem + C::OFF_IN);
         const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0;
-        if (vec) {
+        if (use_tma) {
+            // fp32 planes in shared memory -> fp16, 8 channels = one 16-byte row per pixel.  Consecutive threads take
+            // consecutive pixels: 4-byte reads and 16-byte writes are both bank-conflict free.
+            mbar_wait(bar_in, 0);
+            const float* st = reinterpret_cast<const float*>(smem + C::OFF_STAGE);
+            constexpr int PS = (TH + 4) * PW;                 // plane stride: [plane][y][x] with x = p & 63, y = p >> 6
+            for (int p = tid; p < (TH + 4) * PW; p += THREADS) {
+                const float* a = st + p;
+                in[p] = pack8(a[0], a[PS], a[2 * PS], a[3 * PS], a[4 * PS], a[5 * PS], a[6 * PS], a[7 * PS]);
+            }
+            for (int p = (TH + 4) * PW + tid; p < C::IN_PX; p += THREADS) in[p] = make_uint4(0, 0, 0, 0);
+        } else if (vec) {
             // item = (row y, aligned group of 4 pixels): gx0 = bx - 4 + 4g covers tile-local x = 4g-2 .. 4g+1
             constexpr int GROUPS = PW / 4 + 1;
             for (int it = tid; it < (TH + 4) * GROUPS; it += THREADS) {
@@ -567,6 +599,22 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
     }
 }
 
+// Tensor map of an aux buffer [8][H][W] fp32 for the kernel's input-tile load: dims (W, H, 8), box (64, TH+4, 8), zero fill.
+// Returns false when the buffer cannot be described (row pitch or base not 16-byte aligned): the kernel then stages through
+// registers.  Pure host-side encoding (a few hundred ns), done per launch.
+static bool make_aux_map(CUtensorMap* tm, const float* aux, int W, int H, int th) {
+    if ((W & 3) != 0 || (reinterpret_cast<uintptr_t>(aux) & 15) != 0) return false;
+    static const bool off = [] { const char* e = getenv("RTO_NET_TMA"); return e && e[0] == '0'; }();   // A/B switch
+    if (off) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, 8};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)tc::PW, (cuuint32_t)(th + 4), 8};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(aux), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int TH>
 static cudaError_t launch_net_th(const NetDev& net, const void* packed, const DenoiseArgs& d, int rows, bool exp_guidance, cudaStream_t stream) {
     // per device: the opt-in shared-memory size is a per-device function attribute.  Atomic flags: several host threads may
@@ -582,8 +630,11 @@ static cudaError_t launch_net_th(const NetDev& net, const void* packed, const De
         attr_set[dev] = true;
     }
     dim3 grid((d.W + tc::TW - 1) / tc::TW, (rows + TH - 1) / TH);
-    guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(static_cast<const unsigned char*>(packed), d, net.fused_bias,
-                                                                                       exp_guidance ? 1 : 0);
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    const bool use_tma = make_aux_map(&tm, d.aux, d.W, d.H, TH);
+    guidance_net_tc_kernel<TH><<<grid, tc::THREADS, tc::Cfg<TH>::SMEM_BYTES, stream>>>(tm, static_cast<const unsigned char*>(packed), d, net.fused_bias,
+                                                                                       exp_guidance ? 1 : 0, use_tma ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -68,10 +68,14 @@ struct Cfg {
     static constexpr int OFF_XCH = OFF_BIAS + 40 * 4;                       // epilogue-2 neighbour exchange: [team][parity][pair][dir][8] floats
     static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 2 * 2 * 32;            // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights | input tile
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES + 2);
-    // fp32 input tile as the tensor-map TMA load delivers it: [8 planes][TH+4 rows][64 px].  It lives where the conv1
-    // activations go later (OFF_MID): it is consumed (converted to fp16, pixel-major) before the first MMA is issued.
+    // fp32 input tile as the tensor-map TMA load delivers it: [8 planes][TH+4 rows][SW px].  The box starts at image column
+    // bx - 4, not bx - 2: a tiled TMA load needs a 16-byte aligned start in the innermost dimension (probed on B200,
+    // tools/probe/tma3d_probe.cu: x0 = -2 faults, x0 = -4 zero-fills), so the rows are SW = 68 floats and tile column x sits at
+    // staging column x + 2.  The tile lives where the conv1 activations go later (OFF_MID): it is consumed (converted to fp16,
+    // pixel-major) before the first MMA is issued.
     static constexpr int OFF_STAGE = OFF_MID;
-    static constexpr int STAGE_BYTES = 8 * (TH + 4) * PW * 4;
+    static constexpr int SW = PW + 4;
+    static constexpr int STAGE_BYTES = 8 * (TH + 4) * SW * 4;
     static_assert(STAGE_BYTES <= 4 * MID_PX * 16 && OFF_STAGE % 128 == 0, "the fp32 staging tile fits the activation buffer, 128-byte aligned");
     static constexpr int SMEM_BYTES = OFF_TMEM + 8;
     static_assert(N1_TILES * 32 <= TMEM_COLS, "conv1 accumulators must fit the TMEM allocation");
@@ -245,7 +249,7 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         if (use_tma) {   // the whole fp32 input tile: 8 planes x (TH+4) rows x 64 px starting at image (bx-2, by-2), zero outside
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_in), "n"(C::STAGE_BYTES) : "memory");
-            tma_load_3d(s_base + C::OFF_STAGE, &aux_map, bx - 2, by - 2, 0, bar_in);
+            tma_load_3d(s_base + C::OFF_STAGE, &aux_map, bx - 4, by - 2, 0, bar_in);
         }
         // packed weights + biases: two bulk async copies (TMA engine, no registers, no thread instructions) signalling bar_w
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_w), "n"(PK_BYTES) : "memory");
@@ -263,9 +267,9 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
             // consecutive pixels: 4-byte reads and 16-byte writes are both bank-conflict free.
             mbar_wait(bar_in, 0);
             const float* st = reinterpret_cast<const float*>(smem + C::OFF_STAGE);
-            constexpr int PS = (TH + 4) * PW;                 // plane stride: [plane][y][x] with x = p & 63, y = p >> 6
+            constexpr int PS = (TH + 4) * C::SW;              // plane stride of [plane][y][column]
             for (int p = tid; p < (TH + 4) * PW; p += THREADS) {
-                const float* a = st + p;
+                const float* a = st + (p >> 6) * C::SW + (p & (PW - 1)) + 2;   // tile pixel (x = p & 63, y = p >> 6) = staging column x + 2
                 in[p] = pack8(a[0], a[PS], a[2 * PS], a[3 * PS], a[4 * PS], a[5 * PS], a[6 * PS], a[7 * PS]);
             }
             for (int p = (TH + 4) * PW + tid; p < C::IN_PX; p += THREADS) in[p] = make_uint4(0, 0, 0, 0);
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
     }
 }
 
-// Tensor map of an aux buffer [8][H][W] fp32 for the kernel's input-tile load: dims (W, H, 8), box (64, TH+4, 8), zero fill.
+// Tensor map of an aux buffer [8][H][W] fp32 for the kernel's input-tile load: dims (W, H, 8), box (68, TH+4, 8), zero fill.
 // Returns false when the buffer cannot be described (row pitch or base not 16-byte aligned): the kernel then stages through
 // registers.  Pure host-side encoding (a few hundred ns), done per launch.
 static bool make_aux_map(CUtensorMap* tm, const float* aux, int W, int H, int th) {
@@ -608,7 +612,7 @@ static bool make_aux_map(CUtensorMap* tm, const float* aux, int W, int H, int th
     if (off) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, 8};
     const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)tc::PW, (cuuint32_t)(th + 4), 8};
+    const cuuint32_t box[3] = {(cuuint32_t)tc::PW + 4, (cuuint32_t)(th + 4), 8};
     const cuuint32_t estr[3] = {1, 1, 1};
     return cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(aux), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,

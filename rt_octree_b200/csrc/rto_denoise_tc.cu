@@ -265,6 +265,7 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
         if (use_tma) {
             // fp32 planes in shared memory -> fp16, 8 channels = one 16-byte row per pixel.  Consecutive threads take
             // consecutive pixels: 4-byte reads and 16-byte writes are both bank-conflict free.
+            __syncthreads();         // bar_in was initialised by thread 32 a moment ago
             mbar_wait(bar_in, 0);
             const float* st = reinterpret_cast<const float*>(smem + C::OFF_STAGE);
             constexpr int PS = (TH + 4) * C::SW;              // plane stride of [plane][y][column]

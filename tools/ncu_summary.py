@@ -13,7 +13,11 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__warps_eligible.avg.per_cycle_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_tensor.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'smsp__pcsamp_warps_issue_stalled_long_scoreboard', 'sm__cycles_elapsed.max']
+        'smsp__pcsamp_warps_issue_stalled_long_scoreboard', 'sm__cycles_elapsed.max',
+        'lts__t_sectors.sum', 'lts__t_sectors.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sectors.sum', 'l1tex__t_requests.sum',
+        'sm__inst_executed.avg.per_cycle_elapsed', 'sm__inst_issued.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.avg.per_cycle_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']
 STALL = 'smsp__average_warps_issue_stalled_'
 
 

@@ -466,6 +466,34 @@ def test_cli_tile_split_matches_full_frame(cli, tmp_path, mid_tree, net_weights,
         _same_files(a, b, names)
 
 
+@pytest.mark.gpu
+def test_cli_pipeline_throughput_close_to_the_api(cli):
+    """The drop-in CLI delivers the pipelined throughput itself: `volrend_headless --pipe 8 --readback rgba8` on the bench
+    workload (tree.npz and poses read from disk, RGBA8 frames into a pinned ring) runs at the rate of the same loop driven
+    through the C ABI from Python (bench.py's e2e).  The measured ratio is printed (target: within 5 %); the assertion is
+    looser so that a noisy neighbour on the box cannot fail the suite."""
+    import cli_bench
+
+    files = cli_bench.workload_files(os.path.join(cli_bench.bench.CACHE, "cli"))
+    pipe = cli_bench.run_cli(files, ["--pipe", "8", "--readback", "rgba8"], 600)
+    serial = cli_bench.run_cli(files, [], 400)
+    import torch
+
+    from rt_octree_b200 import capi, synthetic as S
+
+    b = cli_bench.bench
+    tree = b.load_tree()
+    poses, fx = b.workload_poses()
+    rig = b.Rig(capi, torch, tree, S.make_guidance_weights(0), b.W, b.H, fx, b.SPP, True, poses, 8)
+    e = rig.e2e(list(range(b.N_POSES)), 8, "rgba8", 10, 0.5, lambda: None, graph=True)
+    api = e["frames"] / e["seconds"]
+    rig.close()
+    print("CLI --pipe 8: %.0f frames/s, C ABI from Python: %.0f frames/s (ratio %.3f); CLI serial protocol %.0f FPS, wall %.0f"
+          % (pipe["fps"], api, pipe["fps"] / api, serial["fps"], serial["wall_fps"]))
+    assert pipe["fps"] > 0.85 * api
+    assert pipe["fps"] > 1.3 * serial["wall_fps"]          # the pipeline is what the product ships, not a bench.py artefact
+
+
 def _llff_dataset(root, n=5):
     from rt_octree_b200 import synthetic as S
 

@@ -19,3 +19,4 @@ try:
 except Exception as e:
     print('bench parse failed', e); print(open('gpurun_out/scale_$N.err').read()[-1500:])
 PY
+timeout 900 python tools/cli_bench.py --gpus $N --pipe 8 --frames 600 > gpurun_out/cli_bench_$N.json 2> gpurun_out/cli_bench_$N.err; echo "cli bench exit $?"; cat gpurun_out/cli_bench_$N.json | cut -c1-1200

@@ -21,6 +21,6 @@ timeout 600 ncu --set full --clock-control none -k regex:"guidance_net|filter_se
     python tools/profile_run.py tt 10 > gpurun_out/ncu_denoise_tt.log 2>&1
 ncu -i gpurun_out/r02_denoise_tt.ncu-rep --page raw --csv > gpurun_out/r02_denoise_tt.raw.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/r02_denoise_tt.raw.csv > gpurun_out/r02_denoise_tt_ncu_full.txt
-rm -f gpurun_out/*.raw.csv
+rm -f gpurun_out/*.raw.csv gpurun_out/r02_render_spp1.ncu-rep gpurun_out/r02_render_tt.ncu-rep gpurun_out/r02_denoise_tt.ncu-rep   # gpurun_out is capped at 64 MiB
 ls -la gpurun_out | head -40
 head -30 gpurun_out/r02_render_bench_ncu_full.txt

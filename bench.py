@@ -317,9 +317,10 @@ class Rig:
             graphs = self.frames_cache[key]["frames"]
             plain_frame = self.frame
 
+            pose_c = [self.capi.Frame.pose_array(p) for p in self.poses]
+
             def gframe(slot, f):
-                self.ctxs[slot].rng_set_frame(f, WARMUP_RNG)
-                graphs[slot].launch(self.poses[f % len(self.poses)], stream=self.streams[slot].cuda_stream)
+                graphs[slot].launch_indexed(pose_c[f % len(pose_c)], f, WARMUP_RNG, self.streams[slot].cuda_stream)
 
             self.frame = gframe
             try:
@@ -391,15 +392,16 @@ class Rig:
             self.frames_cache[key] = {"bufs": bufs, "frames": frames}
         bufs, frames = self.frames_cache[key]["bufs"], self.frames_cache[key]["frames"]
         host_poses = np.ascontiguousarray(self.poses)            # pageable host memory, read per step
+        pose_c = [capi.Frame.pose_array(p) for p in host_poses]  # ... as the ctypes arrays the frame launch takes
 
         def one(i, f):
             k = i % n_slots
             c, st = self.ctxs[k], self.streams[k]
             st.synchronize()                                     # slot k is free again (its previous copy has landed)
-            c.rng_set_frame(f, WARMUP_RNG)
             if graph:
-                frames[k].launch(host_poses[f % len(host_poses)], stream=st.cuda_stream)
+                frames[k].launch_indexed(pose_c[f % len(pose_c)], f, WARMUP_RNG, st.cuda_stream)   # rng for pose f + ONE graph launch
                 return
+            c.rng_set_frame(f, WARMUP_RNG)
             self.cam.transform = host_poses[f % len(host_poses)]
             capi.launch_renderer(self.tree, self.cam, self.opt, c, stream=st.cuda_stream)
             if self.net:
@@ -564,6 +566,30 @@ def run_cuda_arm(args):
         except Exception as e:  # a side measurement must not take the headline down
             extras["config5_4k_tile_split"] = {"unavailable": repr(e)[:300]}
 
+    if not args.no_extras and not args.no_cli:
+        # ---- the PRODUCT's own end to end: volrend_headless --pipe 8 --readback rgba8 on the same workload read from disk
+        #      (tree.npz, transforms json), frame-sharded over all `world` GPUs by the C++ driver itself (one host thread per
+        #      GPU).  Rank 0 runs it while the other ranks wait; their GPUs are idle meanwhile.
+        barrier()
+        if rank == 0:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import cli_bench
+
+                files = cli_bench.workload_files(os.path.join(CACHE, "cli"))
+                flags = ["--pipe", "8", "--readback", "rgba8"] + (["--num_gpus", str(world)] if world > 1 else [])
+                r = cli_bench.run_cli(files, flags, 600 * world)
+                extras["e2e_cli_pipe8"] = {"value": r.get("aggregate_wall_fps", r.get("fps")), "unit": "frames/s", "n_gpus": world,
+                                           "command": "volrend_headless tree.npz transforms_test.json --options opt.json --ts_module w "
+                                                      + " ".join(flags), "d2h_bytes_per_step": W * H * 4,
+                                           "note": "wall clock of the C++ driver's timed loop (slowest shard), RGBA8 frames into pinned host memory"}
+                if world == 1:
+                    r1 = cli_bench.run_cli(files, [], 400)
+                    extras["cli_serial_protocol"] = {"fps_stage_sum": r1.get("fps"), "fps_wall": r1.get("wall_fps"),
+                                                     "command": "volrend_headless ... (no --pipe: the reference's one-stream protocol)"}
+            except Exception as e:
+                extras["e2e_cli_pipe8"] = {"unavailable": repr(e)[:300]}
+        barrier()
     if rank == 0:
         peaks = {}
         try:
@@ -651,6 +677,7 @@ def main():
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / reference_cuda side measurements")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (SPP 1, T&T 1080p, write_buffer, tile split)")
     ap.add_argument("--no-tt", action="store_true", help="skip BASELINE config 4 (saves the depth-10 tree generation)")
+    ap.add_argument("--no-cli", action="store_true", help="skip the volrend_headless --pipe measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

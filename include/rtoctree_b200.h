@@ -266,6 +266,9 @@ typedef struct rto_frame_desc {
 } rto_frame_desc;
 int rto_frame_create(rto_frame** out, rto_context* ctx, const rto_frame_desc* desc);
 int rto_frame_launch(rto_frame* frame, const float c2w[12], void* stream);
+/* rto_context_rng_set_frame(ctx, warmup, frame_index) + rto_frame_launch in one call: the whole per-frame host work of a
+ * frame-sharded or pipelined driver (pose `frame_index` of the job, rng state as main_headless.cpp leaves it for that pose) */
+int rto_frame_launch_indexed(rto_frame* frame, const float c2w[12], int64_t warmup, int64_t frame_index, void* stream);
 void rto_frame_destroy(rto_frame* frame);
 
 /* ---- timer : RenderContext::Timer (render_context.hpp:122-213) ----

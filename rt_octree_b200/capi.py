@@ -64,7 +64,7 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_net_create", "rto_net_destroy", "rto_net_set_impl", "rto_net_set_bias_mode", "rto_denoise", "rto_denoise_rows", "rto_net_forward",
     "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
     "rto_context_image_rgba8", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
-    "rto_frame_create", "rto_frame_launch", "rto_frame_destroy",
+    "rto_frame_create", "rto_frame_launch", "rto_frame_launch_indexed", "rto_frame_destroy",
     "rto_context_set_image_target", "rto_context_mark_image_written", "rto_peer_enable", "rto_ipc_export", "rto_ipc_open",
     "rto_ipc_close", "rto_event_create", "rto_event_record", "rto_stream_wait_event", "rto_event_destroy",
 ]
@@ -133,6 +133,7 @@ def load(path: str = LIB_PATH):
     L.rto_host_free.argtypes = [P]
     L.rto_frame_create.argtypes = [C.POINTER(P), P, C.POINTER(FrameDescPOD)]
     L.rto_frame_launch.argtypes = [P, C.POINTER(C.c_float * 12), P]
+    L.rto_frame_launch_indexed.argtypes = [P, C.POINTER(C.c_float * 12), C.c_int64, C.c_int64, P]
     L.rto_frame_destroy.argtypes = [P]
     L.rto_frame_destroy.restype = None
     L.rto_context_set_image_target.argtypes = [P, P, P]
@@ -623,10 +624,23 @@ class Frame:
                          rgba8.ptr if rgba8 is not None else None, image.ptr if image is not None else None,
                          aux.ptr if aux is not None else None)
         _check(load().rto_frame_create(C.byref(self._h), ctx._h, C.byref(d)))
+        self._launch_indexed = load().rto_frame_launch_indexed
+
+    @staticmethod
+    def pose_array(c2w12):
+        """A camera transform as the ctypes array the launch calls take (build once per pose, reuse per frame)."""
+        return (C.c_float * 12)(*[float(v) for v in np.asarray(c2w12, np.float32).reshape(12)])
 
     def launch(self, c2w12, stream=0):
-        m = (C.c_float * 12)(*[float(v) for v in np.asarray(c2w12, np.float32).reshape(12)])
+        m = c2w12 if isinstance(c2w12, C.c_float * 12) else self.pose_array(c2w12)
         _check(load().rto_frame_launch(self._h, C.byref(m), C.c_void_p(stream)))
+
+    def launch_indexed(self, c2w12, frame, warmup=100, stream=0):
+        """ctx.rng for pose `frame` of the job (rng_set_frame) + launch, one library call."""
+        m = c2w12 if isinstance(c2w12, C.c_float * 12) else self.pose_array(c2w12)
+        rc = self._launch_indexed(self._h, m, warmup, frame, stream)
+        if rc != RTO_OK:
+            _check(rc)
 
     def close(self):
         if self._h:

@@ -819,6 +819,12 @@ int rto_frame_launch(rto_frame* f, const float c2w[12], void* stream) {
     return RTO_OK;
 }
 
+int rto_frame_launch_indexed(rto_frame* f, const float c2w[12], int64_t warmup, int64_t frame, void* stream) {
+    if (!f) return fail(RTO_ERR_INVALID, "NULL argument");
+    if (int rc = rto_context_rng_set_frame(f->ctx, warmup, frame)) return rc;
+    return rto_frame_launch(f, c2w, stream);
+}
+
 void rto_frame_destroy(rto_frame* f) {
     if (!f) return;
     if (f->exec) cudaGraphExecDestroy(f->exec);

@@ -607,15 +607,36 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 // Tensor map of an aux buffer [8][H][W] fp32 for the kernel's input-tile load: dims (W, H, 8), box (68, TH+4, 8), zero fill.
 // Returns false when the buffer cannot be described (row pitch or base not 16-byte aligned): the kernel then stages through
 // registers.  Pure host-side encoding (a few hundred ns), done per launch.
+// cuTensorMapEncodeTiled is a DRIVER entry point: it is looked up through the runtime (cudaGetDriverEntryPoint) so that the
+// library carries no link-time dependency on libcuda.so.1 and still loads — and fails loudly at the first compute call — on
+// a machine without a driver (tests/test_abi.py::test_no_gpu_fails_loudly).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
 static bool make_aux_map(CUtensorMap* tm, const float* aux, int W, int H, int th) {
     if ((W & 3) != 0 || (reinterpret_cast<uintptr_t>(aux) & 15) != 0) return false;
+    const EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return false;
     static const bool off = [] { const char* e = getenv("RTO_NET_TMA"); return e && e[0] == '0'; }();   // A/B switch
     if (off) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, 8};
     const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
     const cuuint32_t box[3] = {(cuuint32_t)tc::PW + 4, (cuuint32_t)(th + 4), 8};
     const cuuint32_t estr[3] = {1, 1, 1};
-    return cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(aux), dims, strides, box, estr,
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(aux), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

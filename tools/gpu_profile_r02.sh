@@ -6,7 +6,7 @@ python tools/profile_run.py bench 2 > /dev/null 2>&1   # generate + cache the tr
 python tools/profile_run.py tt 2 > /dev/null 2>&1
 # launch list of one bench.py step sequence (per-launch durations; shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r02_launches.csv \
-    python bench.py --steps 12 --warmup 3 --no-baselines --no-extras --min-seconds 0.01 > gpurun_out/ncu_bench.log 2>&1
+    python bench.py --steps 12 --warmup 3 --no-baselines --no-extras --no-cli --min-seconds 0.01 > gpurun_out/ncu_bench.log 2>&1
 for cfg in bench spp1 tt; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 6 -c 2 -f -o gpurun_out/r02_render_$cfg \
       python tools/profile_run.py $cfg 10 > gpurun_out/ncu_render_$cfg.log 2>&1

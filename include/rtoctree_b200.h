@@ -239,6 +239,8 @@ int rto_ipc_export(const void* dev_ptr, unsigned char handle[64]);    /* cudaIpc
 int rto_ipc_open(const unsigned char handle[64], void** dev_ptr);     /* cudaIpcOpenMemHandle, peer access enabled lazily */
 int rto_ipc_close(void* dev_ptr);
 int rto_event_create(void** event);                                    /* cross-stream / cross-device ordering without host syncs */
+int rto_event_create_timed(void** event);                              /* with timing: per-band device times for the band balancer */
+int rto_event_elapsed_ms(void* start, void* end, float* ms);           /* waits for `end`, then cudaEventElapsedTime */
 int rto_event_record(void* event, void* stream);
 int rto_stream_wait_event(void* stream, void* event);
 int rto_event_destroy(void* event);

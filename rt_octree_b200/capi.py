@@ -66,7 +66,8 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_context_image_rgba8", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
     "rto_frame_create", "rto_frame_launch", "rto_frame_launch_indexed", "rto_frame_destroy",
     "rto_context_set_image_target", "rto_context_mark_image_written", "rto_peer_enable", "rto_ipc_export", "rto_ipc_open",
-    "rto_ipc_close", "rto_event_create", "rto_event_record", "rto_stream_wait_event", "rto_event_destroy",
+    "rto_ipc_close", "rto_event_create", "rto_event_create_timed", "rto_event_elapsed_ms", "rto_event_record", "rto_stream_wait_event",
+    "rto_event_destroy",
 ]
 
 _lib = None
@@ -143,6 +144,8 @@ def load(path: str = LIB_PATH):
     L.rto_ipc_open.argtypes = [P, C.POINTER(P)]
     L.rto_ipc_close.argtypes = [P]
     L.rto_event_create.argtypes = [C.POINTER(P)]
+    L.rto_event_create_timed.argtypes = [C.POINTER(P)]
+    L.rto_event_elapsed_ms.argtypes = [P, P, C.POINTER(F)]
     L.rto_event_record.argtypes = [P, P]
     L.rto_stream_wait_event.argtypes = [P, P]
     L.rto_event_destroy.argtypes = [P]

@@ -669,6 +669,19 @@ int rto_event_create(void** event) {
     *event = (void*)e;
     return RTO_OK;
 }
+int rto_event_create_timed(void** event) {
+    if (!event) return fail(RTO_ERR_INVALID, "event is NULL");
+    cudaEvent_t e = nullptr;
+    RTO_CUDA(cudaEventCreate(&e));
+    *event = (void*)e;
+    return RTO_OK;
+}
+int rto_event_elapsed_ms(void* start, void* end, float* ms) {
+    if (!start || !end || !ms) return fail(RTO_ERR_INVALID, "NULL argument");
+    RTO_CUDA(cudaEventSynchronize((cudaEvent_t)end));
+    RTO_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)end));
+    return RTO_OK;
+}
 int rto_event_record(void* event, void* stream) {
     RTO_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
     return RTO_OK;

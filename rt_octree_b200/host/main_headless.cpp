@@ -462,6 +462,29 @@ class SpinBarrier {
     std::atomic<int> count_{0}, gen_{0};
 };
 
+// Band balancer of the tile split: the bands through the object cost more than the top and bottom ones, and the frame is as
+// slow as its slowest band.  After every frame each band reports its device time; the cost per row is taken as constant
+// inside a band, the cumulative cost is cut into equal parts and the boundaries move half way to those cuts (damping: poses
+// change from frame to frame).  Any partition of the rows gives the same pixels, so this is purely a scheduling decision.
+std::vector<int> rebalance_bands(const std::vector<int>& bounds, const std::vector<float>& ms, int H, int min_rows = 16) {
+    const int n = (int)ms.size();
+    std::vector<double> cum(n + 1, 0.0);
+    for (int g = 0; g < n; ++g) cum[g + 1] = cum[g] + std::max(1e-6, (double)ms[g]);
+    std::vector<int> out(bounds);
+    for (int k = 1; k < n; ++k) {
+        const double target = cum[n] * k / n;
+        int g = 0;
+        while (g + 1 < n && cum[g + 1] < target) ++g;
+        const double frac = (target - cum[g]) / (cum[g + 1] - cum[g]);
+        const double y = bounds[g] + frac * (bounds[g + 1] - bounds[g]);
+        out[k] = (int)std::lround(0.5 * bounds[k] + 0.5 * y);
+    }
+    for (int k = 1; k < n; ++k) out[k] = std::max(out[k], out[k - 1] + min_rows);
+    for (int k = n - 1; k >= 1; --k) out[k] = std::min(out[k], out[k + 1] - min_rows);
+    out[0] = 0; out[n] = H;
+    return out;
+}
+
 // --tile_split: single-frame latency mode.  One host thread per GPU; for every frame each thread renders the
 // rows of its band plus the denoiser's halo (2 rows for the two 3x3 convolutions + L for the largest filter level), runs the
 // GuidanceNet and the filter on its band, and the filter's epilogue stores the band directly into GPU 0's image (float4 and
@@ -478,7 +501,11 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
     float* dst_img = nullptr;          // GPU 0's image / RGBA8 copy: the destination of every band
     unsigned char* dst_img8 = nullptr;
     int levels = 4;
-    std::vector<double> lat_ms;
+    std::vector<double> lat_ms, dev_ms;
+    std::vector<int> bounds(n + 1);                  // band g = rows [bounds[g], bounds[g+1]); equal heights to start with
+    for (int g = 0; g <= n; ++g) bounds[g] = (int)((int64_t)H * g / n);
+    std::vector<float> band_ms(n, 1.f);
+    const bool balance = n > 1 && !getenv("RTO_TILE_SPLIT_STATIC");
     const rto_render_options opt = job.options.pod();
     auto worker = [&](int g) {
         try {
@@ -493,6 +520,9 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
             void* stream = nullptr;
             rto_check(rto_stream_create(&stream), "stream");
             rto_check(rto_event_create(&events[g]), "event");
+            void *ev_t0 = nullptr, *ev_t1 = nullptr;   // device time of this band (for the balancer)
+            rto_check(rto_event_create_timed(&ev_t0), "event");
+            rto_check(rto_event_create_timed(&ev_t1), "event");
             uint8_t* h8 = nullptr;
             float *himg = nullptr, *haux = nullptr;
             if (g == 0) {
@@ -508,17 +538,19 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
                 rto_check(rto_context_set_image_target(ctx.handle, dst_img, dst_img8), "image target");
             }
             const int halo = job.options.denoise ? 2 + levels : 0;
-            const int b0 = (int)((int64_t)H * g / n), b1 = (int)((int64_t)H * (g + 1) / n);
-            const int r0 = std::max(0, b0 - halo), r1 = std::min(H, b1 + halo);
             rto_camera cam{};
             cam.width = W; cam.height = H; cam.fx = job.fx; cam.fy = job.fy;
             auto one = [&](const Mat43& pose, int64_t warm, int64_t frame, bool timed, size_t out_index) {
                 bar.wait();
                 const auto t0 = std::chrono::steady_clock::now();
+                const int b0 = bounds[g], b1 = bounds[g + 1];
+                const int r0 = std::max(0, b0 - halo), r1 = std::min(H, b1 + halo);
                 memcpy(cam.c2w, pose.m, sizeof cam.c2w);
                 rto_check(rto_context_rng_set_frame(ctx.handle, warm, frame), "rng");
+                rto_check(rto_event_record(ev_t0, stream), "event");
                 rto_check(rto_render_rect(ctx.handle, tree.device, &cam, &opt, 0, r0, W, r1, stream), "render band");
                 if (job.options.denoise) rto_check(rto_denoise_rows(ctx.handle, denoiser.handle(), b0, b1, stream), "denoise band");
+                rto_check(rto_event_record(ev_t1, stream), "event");
                 rto_check(rto_event_record(events[g], stream), "event");
                 bar.wait();   // every band's completion event has been recorded
                 if (g == 0) {
@@ -532,6 +564,13 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
                 } else {
                     rto_check(rto_synchronize(stream), "sync");
                 }
+                // outside the timed window: band times -> next frame's boundaries
+                rto_check(rto_event_elapsed_ms(ev_t0, ev_t1, &band_ms[g]), "band time");
+                bar.wait();
+                if (g == 0) {
+                    if (timed) dev_ms.push_back(*std::max_element(band_ms.begin(), band_ms.end()));
+                    if (balance) bounds = rebalance_bands(bounds, band_ms, H);
+                }
             };
             for (int w = 0; w < job.warmup; ++w) one(job.trans[0], 0, w, false, 0);
             for (size_t i = 0; i < frames; ++i) one(job.trans[i], job.warmup, (int64_t)i, true, i);
@@ -539,6 +578,7 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
             if (g != 0) rto_context_set_image_target(ctx.handle, nullptr, nullptr);
             rto_host_free(h8); rto_host_free(himg); rto_host_free(haux);
             rto_event_destroy(events[g]);
+            rto_event_destroy(ev_t0); rto_event_destroy(ev_t1);
             rto_stream_destroy(stream);
         } catch (const std::exception& e) {
             errors[g] = e.what();
@@ -561,6 +601,11 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
     printf("], %dx%d, halo %d rows, peer-direct stores into the first GPU\n", W, H, job.options.denoise ? 2 + levels : 0);
     printf("latency: median %.6f ms, mean %.6f ms, min %.6f ms per frame (rendezvous -> RGBA8 frame on the host, %zu frames)\n",
            s[s.size() / 2], mean, s.front(), lat_ms.size());
+    std::vector<double> d = dev_ms;
+    std::sort(d.begin(), d.end());
+    printf("slowest band, device time: median %.6f ms (bands %s; last boundaries:", d[d.size() / 2], balance ? "balanced by the previous frame's band times" : "of equal height");
+    for (int g = 0; g <= n; ++g) printf(" %d", bounds[g]);
+    printf(")\n");
     printf("FPS:    %.10f   (1000 / median latency)\n", 1000.0 / s[s.size() / 2]);
 }
 

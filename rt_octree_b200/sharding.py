@@ -46,6 +46,30 @@ def render_rows_for_band(band: Tuple[int, int], height: int, denoise: bool, leve
     return max(0, band[0] - h), min(height, band[1] + h)
 
 
+def rebalance_bands(bounds: List[int], band_ms: List[float], height: int, min_rows: int = 16) -> List[int]:
+    """Band balancer of the tile split (same rule as volrend_headless --tile_split): cost per row constant inside a band,
+    cumulative cost cut into equal parts, boundaries moved half way to those cuts.  bounds has len(band_ms) + 1 entries."""
+    n = len(band_ms)
+    cum = [0.0]
+    for t in band_ms:
+        cum.append(cum[-1] + max(1e-6, float(t)))
+    out = list(bounds)
+    for k in range(1, n):
+        target = cum[n] * k / n
+        g = 0
+        while g + 1 < n and cum[g + 1] < target:
+            g += 1
+        frac = (target - cum[g]) / (cum[g + 1] - cum[g])
+        y = bounds[g] + frac * (bounds[g + 1] - bounds[g])
+        out[k] = int(round(0.5 * bounds[k] + 0.5 * y))
+    for k in range(1, n):
+        out[k] = max(out[k], out[k - 1] + min_rows)
+    for k in range(n - 1, 0, -1):
+        out[k] = min(out[k], out[k + 1] - min_rows)
+    out[0], out[n] = 0, height
+    return out
+
+
 def gather_bands(band_tensor, bands: List[Tuple[int, int]], rank: int, world: int, dst: int = 0, group=None):
     """Gather the per-rank [rows_r, W, 4] final-image bands to `dst` and return the assembled [H, W, 4] frame there
     (None elsewhere).  Bands may differ in height by one row, so they are padded to the tallest band for the collective."""
@@ -93,13 +117,16 @@ class PeerTileSplit:
     into rank 0's memory, followed by one 4-byte all-reduce on the same stream (NCCL: stream-ordered, no host sync) — or,
     with a host-side backend (gloo), a stream synchronise + barrier."""
 
-    def __init__(self, capi, dist, rank: int, world: int, width: int, height: int, levels: int = 4, rgba8: bool = True):
+    def __init__(self, capi, dist, rank: int, world: int, width: int, height: int, levels: int = 4, rgba8: bool = True,
+                 balance: bool = True):
         import torch
 
         self.capi, self.dist, self.rank, self.world = capi, dist, rank, world
         self.levels = levels
+        self.height = height
         self.ctx = capi.RenderContext(width, height)
         self.bands = tile_bands(height, world)
+        self.balance = balance and world > 1
         self._opened = []
         self.nccl = world > 1 and dist.get_backend() == "nccl"
         self.token = torch.zeros(1, dtype=torch.int32, device="cuda") if self.nccl else None
@@ -116,7 +143,7 @@ class PeerTileSplit:
         elif rgba8:
             self.ctx.image_rgba8_ptr   # allocate: the filter then writes the RGBA8 copy as well
 
-    def render(self, tree, net, cam, opt, c2w12, frame: int, warmup: int = 100, stream: int = 0):
+    def render(self, tree, net, cam, opt, c2w12, frame: int, warmup: int = 100, stream: int = 0, band_done=None):
         """Enqueue this rank's share of the frame on `stream`; returns after the completion barrier has been ENQUEUED (nccl)
         or has completed (host backends).  On rank 0 the full frame is then in ctx's image / RGBA8 copy, in stream order."""
         capi, ctx = self.capi, self.ctx
@@ -127,6 +154,8 @@ class PeerTileSplit:
         capi.launch_renderer(tree, cam, opt, ctx, stream=stream, rect=(0, y0, cam.width, y1))   # denoise off: y0, y1 == the band
         if opt.denoise:
             net.denoise(cam, ctx, stream=stream, rows=band)
+        if band_done is not None:
+            band_done.record()                         # torch event on the current stream: this rank's band is done here
         if self.world > 1:
             if self.nccl:
                 self.dist.all_reduce(self.token)       # on torch's current stream: callers pass that stream as `stream`
@@ -135,6 +164,21 @@ class PeerTileSplit:
                 self.dist.barrier()
         if self.rank == 0:
             ctx.mark_image_written(True)
+
+    def report_band_time(self, ms: float):
+        """Call after a frame has completed (outside any timed window) with this rank's device time for its band: every
+        rank learns all band times (one small all-gather) and moves the boundaries for the next frame (rebalance_bands)."""
+        if not self.balance:
+            return
+        import torch
+
+        dev = "cuda" if self.nccl else "cpu"
+        mine = torch.tensor([float(ms)], dtype=torch.float32, device=dev)
+        allt = [torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allt, mine)
+        bounds = [b[0] for b in self.bands] + [self.height]
+        nb = rebalance_bands(bounds, [float(t.item()) for t in allt], self.height)
+        self.bands = [(nb[r], nb[r + 1]) for r in range(self.world)]
 
     def close(self):
         if self.rank != 0:
@@ -171,8 +215,9 @@ def bench_tile_split(capi, torch, dist, tree, weights, poses, rank, world, local
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        eb = torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        ts.render(t, net, cam, opt, poses[f % len(poses)], f, warmup_rng, stream=sp)
+        ts.render(t, net, cam, opt, poses[f % len(poses)], f, warmup_rng, stream=sp, band_done=eb)
         e1.record(st)
         if rank == 0:
             ts.ctx.read_image_rgba8(host8.array, stream=sp, sync=False)
@@ -180,6 +225,7 @@ def bench_tile_split(capi, torch, dist, tree, weights, poses, rank, world, local
         if f >= 3:
             lat.append(time.perf_counter() - t0)
             dev_ms.append(e0.elapsed_time(e1))
+        ts.report_band_time(e0.elapsed_time(eb))       # outside the timed window: next frame's band boundaries
     identical = None
     if check:
         f = frames + 2

@@ -39,6 +39,27 @@ def test_tile_bands_and_halo():
     assert SH.denoise_halo(4) == SH.DENOISE_HALO == 6 and SH.denoise_halo(6) == 8
 
 
+def test_rebalance_bands():
+    """Band balancer of the tile split: endpoints fixed, boundaries strictly increasing with a minimum band height, and the
+    bands move towards equal cost (iterating on a fixed cost profile converges to it)."""
+    H, n = 2160, 8
+    rows = np.arange(H)
+    density = 1.0 + 3.0 * np.exp(-((rows - 1000.0) / 300.0) ** 2)        # heavy in the middle, like a frame through the object
+    bounds = [H * g // n for g in range(n + 1)]
+    spread0 = None
+    for it in range(12):
+        ms = [float(density[bounds[g]:bounds[g + 1]].sum()) for g in range(n)]
+        if spread0 is None:
+            spread0 = max(ms) / min(ms)
+        bounds = SH.rebalance_bands(bounds, ms, H)
+        assert bounds[0] == 0 and bounds[-1] == H and all(bounds[g + 1] - bounds[g] >= 16 for g in range(n))
+    ms = [float(density[bounds[g]:bounds[g + 1]].sum()) for g in range(n)]
+    assert spread0 > 2.5 and max(ms) / min(ms) < 1.1
+    # degenerate inputs: zero times, two bands, tiny image
+    assert SH.rebalance_bands([0, 50, 100], [0.0, 0.0], 100) == [0, 50, 100]
+    assert SH.rebalance_bands([0, 20, 40], [1.0, 100.0], 40) == [0, 24, 40]      # min_rows keeps both bands >= 16 rows
+
+
 def _worker(rank, world, port, H, W, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -20,3 +20,12 @@ except Exception as e:
     print('bench parse failed', e); print(open('gpurun_out/scale_$N.err').read()[-1500:])
 PY
 timeout 900 python tools/cli_bench.py --gpus $N --pipe 8 --frames 600 > gpurun_out/cli_bench_$N.json 2> gpurun_out/cli_bench_$N.err; echo "cli bench exit $?"; cat gpurun_out/cli_bench_$N.json | cut -c1-1200
+# the product binary's own tile split: 3840x2160, bands over the N GPUs, balanced and static, 60 poses
+C=/tmp/rto_cache/cli
+for mode in balanced static; do
+  if [ "$mode" = static ]; then export RTO_TILE_SPLIT_STATIC=1; else unset RTO_TILE_SPLIT_STATIC; fi
+  timeout 600 rt_octree_b200/bin/volrend_headless $C/tree.npz $C/transforms_test.json --options $C/opt.json --ts_module $C/ts_latest.ts \
+      -w 3840 -h 2160 --warmup 20 --max_imgs 60 --tile_split --num_gpus $N > gpurun_out/cli_tile_split_${N}_$mode.txt 2>&1
+  echo "cli tile split ($mode) exit $?"; grep -E "tile split:|latency:|slowest band" gpurun_out/cli_tile_split_${N}_$mode.txt
+done
+unset RTO_TILE_SPLIT_STATIC

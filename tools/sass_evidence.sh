@@ -12,13 +12,14 @@ cuobjdump -sass "$LIB" > "$TMP"
 {
   echo "# cuobjdump -sass $LIB   ($(date -u +%Y-%m-%d), $(nvcc --version | tail -2 | head -1))"
   echo "# sm_100a mnemonics: UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit,"
-  echo "# UTCATOMSWS = tcgen05.alloc/dealloc, UBLKCP.S.G = cp.async.bulk global -> shared (TMA engine), SYNCS.* = mbarrier ops"
+  echo "# UTCATOMSWS = tcgen05.alloc/dealloc, UBLKCP.S.G = cp.async.bulk global -> shared (TMA engine, 1-D: weights),"
+  echo "# UTMALDG = cp.async.bulk.tensor (tensor-map TMA: the fp32 input tile), SYNCS.* = mbarrier ops"
   echo
   echo "## per kernel: tensor-core / TMEM / TMA / mbarrier instruction counts"
   awk '/Function : /{name=$3} /UTCHMMA|LDTM|UBLKCP|UTCBAR|UTCATOMSWS|UTMALDG|SYNCS\./{ match($0, /(UTCHMMA|LDTM|UBLKCP|UTCBAR|UTCATOMSWS|UTMALDG|SYNCS)[.A-Za-z0-9_]*/); k=name " " substr($0, RSTART, RLENGTH); c[k]++ } END{for (k in c) print c[k], k}' "$TMP" | sort -k2,2 -k3,3 | c++filt
   echo
-  echo "## guidance_net_tc_kernel<10>: every UTCHMMA / UTCBAR / LDTM / UBLKCP / UTCATOMSWS line (address, instruction)"
-  awk '/Function : .*guidance_net_tc_kernelILi10E/{p=1; next} /Function : /{p=0} p && /UTCHMMA|LDTM|UBLKCP|UTCBAR|UTCATOMSWS/ && !/^\s*\/\* 0x/{print}' "$TMP" | sed 's/ *\/\* 0x[0-9a-f]* \*\/ *$//' | head -80
+  echo "## guidance_net_tc_kernel<10>: every UTMALDG / UTCHMMA / UTCBAR / LDTM / UBLKCP / UTCATOMSWS line (address, instruction)"
+  awk '/Function : .*guidance_net_tc_kernelILi10E/{p=1; next} /Function : /{p=0} p && /UTMALDG|UTCHMMA|LDTM|UBLKCP|UTCBAR|UTCATOMSWS/ && !/^\s*\/\* 0x/{print}' "$TMP" | sed 's/ *\/\* 0x[0-9a-f]* \*\/ *$//' | head -80
   echo
   echo "## render_kernel<6,false,3> (production): the marching loop, from the FFMA.SAT position update to the loop branch"
   awk '/Function : _ZN3rto13render_kernelILi6ELb0ELi3EEE/{p=1; next} /Function : /{p=0} p' "$TMP" | grep -v '^\s*/\* 0x' | sed 's/ *\/\* 0x[0-9a-f]* \*\/ *$//' | awk '/FFMA.SAT/ && !s {s=1} s{print} s && /BRA P1/{exit}'

@@ -448,12 +448,18 @@ def run_cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device — the CUDA arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     capi.set_device(local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")   # host-side rendezvous that neither spins a CPU core nor parks a kernel on the GPUs
 
     def barrier():
         if world > 1:
             dist.barrier()
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
 
     def reduce_max(vals):
         t = torch.tensor(vals, device="cuda", dtype=torch.float64)
@@ -569,8 +575,10 @@ def run_cuda_arm(args):
     if not args.no_extras and not args.no_cli:
         # ---- the PRODUCT's own end to end: volrend_headless --pipe 8 --readback rgba8 on the same workload read from disk
         #      (tree.npz, transforms json), frame-sharded over all `world` GPUs by the C++ driver itself (one host thread per
-        #      GPU).  Rank 0 runs it while the other ranks wait; their GPUs are idle meanwhile.
-        barrier()
+        #      GPU).  Rank 0 runs it while the other ranks wait in a HOST-side (gloo) barrier: an NCCL barrier would park a
+        #      polling kernel on every GPU and a spinning thread on every core the C++ driver needs.
+        torch.cuda.synchronize()
+        host_barrier()
         if rank == 0:
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -589,7 +597,7 @@ def run_cuda_arm(args):
                                                      "command": "volrend_headless ... (no --pipe: the reference's one-stream protocol)"}
             except Exception as e:
                 extras["e2e_cli_pipe8"] = {"unavailable": repr(e)[:300]}
-        barrier()
+        host_barrier()
     if rank == 0:
         peaks = {}
         try:

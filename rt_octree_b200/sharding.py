@@ -270,5 +270,7 @@ def bench_tile_split(capi, torch, dist, tree, weights, poses, rank, world, local
            "single_gpu_latency_ms": single_ms, "bit_identical_to_single_gpu": identical,
            "exchange": "filter epilogue stores each band into rank 0's image through a CUDA-IPC peer mapping (NVLink); one 4-byte "
                        "stream-ordered all-reduce signals completion; no gather", "halo_rows": denoise_halo(4),
+           "bands": "balanced by the previous frame's band times" if ts.balance else "equal heights",
+           "last_band_boundaries": [b[0] for b in ts.bands] + [height],
            "d2h_bytes_per_frame": width * height * 4}
     return out

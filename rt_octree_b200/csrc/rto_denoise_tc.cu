@@ -674,9 +674,10 @@ cudaError_t launch_guidance_net_tc(const NetDev& net, const void* packed, const 
     static const int th = [] {   // thread-safe one-time initialisation
         const char* v = getenv("RTO_NET_TILE_H");
         const int t = v ? atoi(v) : 10;
-        return (t == 8 || t == 10 || t == 12 || t == 14) ? t : 10;
+        return (t == 6 || t == 8 || t == 10 || t == 12 || t == 14) ? t : 10;
     }();
     switch (th) {
+        case 6: return launch_net_th<6>(net, packed, d, rows, exp_guidance, stream);
         case 8: return launch_net_th<8>(net, packed, d, rows, exp_guidance, stream);
         case 12: return launch_net_th<12>(net, packed, d, rows, exp_guidance, stream);
         case 14: return launch_net_th<14>(net, packed, d, rows, exp_guidance, stream);

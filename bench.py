@@ -269,6 +269,22 @@ def reference_cuda_fps(tree, poses, fx, weights, frames=40):
         return {"unavailable": repr(e)[:300]}
 
 
+def render_kernel_name(info):
+    """The instantiation launch_spp picks for this tree (rto_render_kernel.cuh): GRID = 10 + K is the fused-index marcher."""
+    off = lambda k: os.environ.get(k, "1")[:1] == "0"
+    if not info.grid_level:
+        g = 0
+    elif off("RTO_GRID8"):
+        g = 1
+    elif off("RTO_DEFER_HITS") or off("RTO_LEAF_PLANES"):
+        g = 2
+    elif off("RTO_FUSED_INDEX"):
+        g = 3
+    else:
+        g = 10 + int(info.grid_level)
+    return "render_kernel<%d,false,%d>" % (SPP, g)
+
+
 class Rig:
     """One workload on this rank: tree + net + a ring of (context, stream) slots, and the three measurements."""
 
@@ -377,7 +393,9 @@ class Rig:
 
     # ---- end to end through the public API with host buffers: the pose comes from host memory, the result lands in pinned
     #      host memory every frame.  Ring of n_slots (context, stream, pinned buffer): the host blocks on the oldest slot only.
-    def e2e(self, my_frames, n_slots, readback, warm, min_s, barrier, graph=True):
+    def e2e(self, my_frames, n_slots, readback, warm, min_s, barrier, graph=True, sequence=True):
+        """sequence (with graph frames): the K-frame block is ONE library call, rto_frame_sequence — the host loop
+        volrend_headless --pipe runs; sequence=False issues one rto_frame_launch_indexed + stream wait per frame from Python."""
         capi, torch, K = self.capi, self.torch, len(my_frames)
         shape, dt = {"rgba8": ((self.h, self.w, 4), np.uint8), "float": ((self.h, self.w, 4), np.float32),
                      "aux": ((8, self.h, self.w), np.float32)}[readback]
@@ -413,12 +431,20 @@ class Rig:
             else:
                 c.read_aux(bufs[k].array, stream=st.cuda_stream, sync=False)
 
+        seq = None
+        if graph and sequence and all(b - a == 1 for a, b in zip(my_frames, my_frames[1:])):
+            seq = capi.FrameSequence(frames, [self.streams[k].cuda_stream for k in range(n_slots)], host_poses, WARMUP_RNG)
+
         def block(reps):
             torch.cuda.synchronize()
             barrier()
             t0 = time.perf_counter()
             i = 0
             for _ in range(reps):
+                if seq is not None:
+                    seq.run(my_frames[0], K)     # K frames: pose + rng per frame, slot waits, graph launches, all inside the library
+                    i += K
+                    continue
                 for f in my_frames:
                     one(i, f)
                     i += 1
@@ -430,7 +456,7 @@ class Rig:
         est, _ = block(1)
         reps = max(1, min(4000, int(math.ceil(min_s / max(est, 1e-6)))))
         sec, n = block(reps)
-        last = bufs[(n - 1) % n_slots].array
+        last = bufs[(my_frames[-1] if seq is not None else n - 1) % n_slots].array
         chk = int(last.sum(dtype=np.int64)) if readback == "rgba8" else float(last.sum(dtype=np.float64))
         return {"seconds": sec, "frames": n, "reps": reps, "checksum": chk, "bytes": int(np.prod(shape)) * np.dtype(dt).itemsize}
 
@@ -505,12 +531,13 @@ def run_cuda_arm(args):
     del flush
 
     e8 = rig.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
+    e8py = rig.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph, sequence=False)
     ef = rig.e2e(my_frames, max(args.pipe, 3), "float", Wm, min_s, barrier, graph=not args.no_graph)
     clk = clocks.stop(t_clk0, t_clk1) if rank == 0 else None
 
-    ms_per_frame, e2e8_ms, e2ef_ms, cold_ms, render_ms, net_ms, filter_ms = reduce_max(
+    ms_per_frame, e2e8_ms, e2ef_ms, cold_ms, render_ms, net_ms, filter_ms, e2e8py_ms = reduce_max(
         [pl["ms_total"] / (pl["reps"] * K), 1e3 * e8["seconds"] / e8["frames"], 1e3 * ef["seconds"] / ef["frames"], cold_ms,
-         sp["render_ms"], sp["net_ms"], sp["filter_ms"]])
+         sp["render_ms"], sp["net_ms"], sp["filter_ms"], 1e3 * e8py["seconds"] / e8py["frames"]])
 
     extras = {}
     if world == 1 and not args.no_extras:
@@ -638,6 +665,9 @@ def run_cuda_arm(args):
             "e2e": {"value": world * 1e3 / e2e8_ms, "unit": "frames/s", "h2d_bytes_per_step": 48 + 28,
                     "d2h_bytes_per_step": W * H * 4, "checksum": e8["checksum"], "frame_slots": NSLOT, "reps": e8["reps"],
                     "timed_region_s": e8["seconds"], "one_graph_launch_per_frame": not args.no_graph,
+                    "api": "rto_frame_sequence: one library call per %d-frame block (pose + rng per frame, slot waits and graph launches "
+                           "inside the library: the host loop of volrend_headless --pipe)" % K if not args.no_graph else "separate launches per frame",
+                    "value_per_frame_calls": world * 1e3 / e2e8py_ms,   # the same ring driven frame by frame from Python (rto_frame_launch_indexed)
                     "readback": "RGBA8 written by the filter epilogue (rto_frame / rto_context_read_image_rgba8), the bytes volrend_headless -o "
                                 "writes to the PNG; the reference converts the same values on the host (main_headless.cpp:524-541)"},
             "e2e_f32": {"value": world * 1e3 / e2ef_ms, "unit": "frames/s", "d2h_bytes_per_step": W * H * 16,
@@ -646,7 +676,7 @@ def run_cuda_arm(args):
                                 "bound by the PCIe link"},
             "gpu_launches": int(pl["launches"]),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "render_kernel<6,0,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": render_kernel_name(info), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": bytes_frame, "per_frame": counters,

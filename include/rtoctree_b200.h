@@ -127,12 +127,13 @@ int rto_tree_create_quantized(rto_tree** out, const int32_t* child, int64_t capa
                               int n_retained);
 /* Copy one device plane of the loaded tree back to the host (inspection / parity tests; the reference keeps the host
  * arrays in N3Tree::data_ / child_ instead).  `bytes` must equal the plane size: nodes = rto_tree_info.node_bytes,
- * payload = payload_bytes, grid top / leaf top = 4 << (3*grid_level), grid bricks / leaf bricks = n_bricks * 2048,
+ * payload = payload_bytes, grid top / leaf top / march top = 4 << (3*grid_level), grid bricks / leaf bricks = n_bricks * 2048,
  * byte bricks = n_bricks * 512 (the leaf planes hold 0 bytes when they were not built). */
 typedef enum rto_tree_plane { RTO_PLANE_NODES = 0, RTO_PLANE_PAYLOAD = 1, RTO_PLANE_GRID_TOP = 2, RTO_PLANE_GRID_BRICKS = 3,
                               RTO_PLANE_GRID_BRICKS8 = 4,
                               RTO_PLANE_GRID_LEAF_TOP = 5,    /* u32 per level-K cell: flat leaf index (node*8+octant) of a leaf cell */
-                              RTO_PLANE_GRID_LEAF_BRICKS = 6  /* u32 per brick cell: flat leaf index of the covering leaf */
+                              RTO_PLANE_GRID_LEAF_BRICKS = 6, /* u32 per brick cell: flat leaf index of the covering leaf */
+                              RTO_PLANE_GRID_MARCH_TOP = 7    /* u32 per level-K cell: leaf word, or brick*512 + 2^18 - (512x + 64y + 8z) */
 } rto_tree_plane;
 int rto_tree_read_plane(const rto_tree* tree, int plane, void* host_dst, size_t bytes);
 /* main_headless.cpp:400-405 / n3tree.hpp:69-71: NDC warp for forward-facing (llff) scenes; width<=0 disables. */
@@ -271,6 +272,17 @@ int rto_frame_launch(rto_frame* frame, const float c2w[12], void* stream);
 /* rto_context_rng_set_frame(ctx, warmup, frame_index) + rto_frame_launch in one call: the whole per-frame host work of a
  * frame-sharded or pipelined driver (pose `frame_index` of the job, rng state as main_headless.cpp leaves it for that pose) */
 int rto_frame_launch_indexed(rto_frame* frame, const float c2w[12], int64_t warmup, int64_t frame_index, void* stream);
+/* The host loop of a pipelined driver in ONE call (volrend_headless --pipe N; main_headless.cpp:441-541 is the serial
+ * original): frame i of [first, first + count) runs on slot k = i % n_slots, i.e. on frames[k] / streams[k], with pose
+ * c2w + 12 * (i % n_poses) and the rng state of pose i (rto_frame_launch_indexed).  Before a slot is reused the call waits
+ * for its stream — the slot's previous frame has reached its pinned host destinations — and, if `retired` is given,
+ * reports that frame as retired(user, frame_index, slot); the callback is the place to consume the host buffers and must
+ * return only when they may be overwritten.  Frames still in flight when the call returns are reported by the next call on
+ * the same slots, or waited for and reported by this one with drain != 0.  Returns the first error; nothing else is launched
+ * after it. */
+typedef void (*rto_frame_retired_fn)(void* user, int64_t frame_index, int slot);
+int rto_frame_sequence(rto_frame* const* frames, void* const* streams, int n_slots, const float* c2w, int64_t n_poses,
+                       int64_t warmup, int64_t first, int64_t count, int drain, rto_frame_retired_fn retired, void* user);
 void rto_frame_destroy(rto_frame* frame);
 
 /* ---- timer : RenderContext::Timer (render_context.hpp:122-213) ----

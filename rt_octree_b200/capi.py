@@ -55,6 +55,9 @@ class FrameDescPOD(C.Structure):
                 ("host_rgba8", C.c_void_p), ("host_image", C.c_void_p), ("host_aux", C.c_void_p)]
 
 
+FRAME_RETIRED_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int)   # rto_frame_retired_fn(user, frame_index, slot)
+
+
 EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py checks the library exports them all)
     "rto_last_error", "rto_abi_version", "rto_set_device", "rto_device_count", "rto_synchronize", "rto_render_options_default",
     "rto_tree_create", "rto_tree_create_quantized", "rto_tree_read_plane", "rto_tree_set_ndc", "rto_tree_get_info", "rto_tree_destroy",
@@ -64,7 +67,7 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_net_create", "rto_net_destroy", "rto_net_set_impl", "rto_net_set_bias_mode", "rto_denoise", "rto_denoise_rows", "rto_net_forward",
     "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
     "rto_context_image_rgba8", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
-    "rto_frame_create", "rto_frame_launch", "rto_frame_launch_indexed", "rto_frame_destroy",
+    "rto_frame_create", "rto_frame_launch", "rto_frame_launch_indexed", "rto_frame_sequence", "rto_frame_destroy",
     "rto_context_set_image_target", "rto_context_mark_image_written", "rto_peer_enable", "rto_ipc_export", "rto_ipc_open",
     "rto_ipc_close", "rto_event_create", "rto_event_create_timed", "rto_event_elapsed_ms", "rto_event_record", "rto_stream_wait_event",
     "rto_event_destroy",
@@ -135,6 +138,7 @@ def load(path: str = LIB_PATH):
     L.rto_frame_create.argtypes = [C.POINTER(P), P, C.POINTER(FrameDescPOD)]
     L.rto_frame_launch.argtypes = [P, C.POINTER(C.c_float * 12), P]
     L.rto_frame_launch_indexed.argtypes = [P, C.POINTER(C.c_float * 12), C.c_int64, C.c_int64, P]
+    L.rto_frame_sequence.argtypes = [C.POINTER(P), C.POINTER(P), I, P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, I, FRAME_RETIRED_FN, P]
     L.rto_frame_destroy.argtypes = [P]
     L.rto_frame_destroy.restype = None
     L.rto_context_set_image_target.argtypes = [P, P, P]
@@ -320,7 +324,8 @@ class N3Tree:
                                      self.data_dim, self.format, self.basis_dim, off, sc))
 
     PLANES = {"nodes": (0, np.uint32), "payload": (1, np.float16), "grid_top": (2, np.uint32), "grid_bricks": (3, np.uint32),
-              "grid_bricks8": (4, np.uint8), "grid_leaf_top": (5, np.uint32), "grid_leaf_bricks": (6, np.uint32)}
+              "grid_bricks8": (4, np.uint8), "grid_leaf_top": (5, np.uint32), "grid_leaf_bricks": (6, np.uint32),
+              "grid_march_top": (7, np.uint32)}
 
     def read_plane(self, name):
         """Device plane copied back to the host (rto_tree_read_plane): nodes / payload / grid_top / grid_bricks."""
@@ -331,7 +336,8 @@ class N3Tree:
                   "grid_bricks": i.n_bricks * 2048 if i.grid_level else 0,
                   "grid_bricks8": i.n_bricks * 512 if i.grid_level else 0,
                   "grid_leaf_top": (4 << (3 * i.grid_level)) if i.grid_level else 0,
-                  "grid_leaf_bricks": i.n_bricks * 2048 if i.grid_level else 0}[name]
+                  "grid_leaf_bricks": i.n_bricks * 2048 if i.grid_level else 0,
+                  "grid_march_top": (4 << (3 * i.grid_level)) if i.grid_level else 0}[name]
         out = np.empty(nbytes // np.dtype(dt).itemsize, dt)
         _check(load().rto_tree_read_plane(self._h, which, out.ctypes.data, nbytes))
         return out
@@ -655,6 +661,29 @@ class Frame:
             self.close()
         except Exception:
             pass
+
+
+class FrameSequence:
+    """rto_frame_sequence: the host loop of a pipelined driver in one library call.  `frames[k]` runs on `streams[k]`
+    (raw stream handles); `poses` is a float32 [n][12] array kept alive here.  run(first, count) issues frames
+    first .. first+count-1 (frame i on slot i % n_slots, pose i % n); `retired(frame_index, slot)` is called when a frame's
+    host buffers are complete, before the slot is reused."""
+
+    def __init__(self, frames, streams, poses, warmup=100, retired=None):
+        self._frames = list(frames)
+        n = len(self._frames)
+        self._fh = (C.c_void_p * n)(*[f._h for f in self._frames])
+        self._st = (C.c_void_p * n)(*[C.c_void_p(s) for s in streams])
+        self._poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+        self._warmup = int(warmup)
+        self._cb = FRAME_RETIRED_FN((lambda user, idx, slot: retired(int(idx), int(slot))) if retired else 0)
+        self._run = load().rto_frame_sequence
+
+    def run(self, first, count, drain=False):
+        rc = self._run(self._fh, self._st, len(self._frames), self._poses.ctypes.data, self._poses.shape[0], self._warmup,
+                       int(first), int(count), 1 if drain else 0, self._cb, None)
+        if rc != RTO_OK:
+            _check(rc)
 
 
 def filtering(weight_ptr, guidance_ptr, img_in_ptr, levels, width, height, img_out_ptr, stream=0):

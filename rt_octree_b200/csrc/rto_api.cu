@@ -31,6 +31,7 @@ struct rto_tree {
     uint8_t* grid_bricks8 = nullptr;   // byte plane of the bricks (depth | dense flag)
     uint32_t* grid_leaf_top = nullptr;     // leaf-id planes: flat leaf index per level-K cell / per brick cell
     uint32_t* grid_leaf_bricks = nullptr;
+    uint32_t* grid_top_m = nullptr;        // march table of the fused-index marcher (rto_ray.cuh FusedIdx)
     int grid_K = 0;
     int64_t n_bricks = 0;
     rto_tree_info info{};
@@ -196,7 +197,7 @@ static int tree_from_source(rto_tree** out, const rto::TreeSource& src, int N, i
     }
     t->nodes = b.nodes; t->payload = b.payload;
     t->grid_top = b.grid_top; t->grid_bricks = b.grid_bricks; t->grid_bricks8 = b.grid_bricks8;
-    t->grid_leaf_top = b.grid_leaf_top; t->grid_leaf_bricks = b.grid_leaf_bricks;
+    t->grid_leaf_top = b.grid_leaf_top; t->grid_leaf_bricks = b.grid_leaf_bricks; t->grid_top_m = b.grid_top_m;
     t->grid_K = b.grid_K; t->n_bricks = b.n_bricks;
     const int64_t n_entries = src.capacity * 8;
     rto_tree_info& I = t->info;
@@ -208,7 +209,7 @@ static int tree_from_source(rto_tree** out, const rto::TreeSource& src, int N, i
     I.grid_level = t->grid_K;
     I.n_bricks = t->n_bricks;
     I.grid_bytes = t->grid_K ? (int64_t)((((size_t)1 << (3 * t->grid_K)) + (size_t)t->n_bricks * 512) * sizeof(uint32_t) * (t->grid_leaf_top ? 2 : 1) +
-                                         (size_t)t->n_bricks * 512) : 0;
+                                         (size_t)t->n_bricks * 512 + (t->grid_top_m ? ((size_t)1 << (3 * t->grid_K)) * sizeof(uint32_t) : 0)) : 0;
     for (int i = 0; i < 3; ++i) { I.offset[i] = offset[i]; I.scale[i] = scale[i]; }
     I.ndc_width = -1.f; I.ndc_height = 0.f; I.ndc_focal = 0.f;
     *out = t;
@@ -256,6 +257,7 @@ int rto_tree_read_plane(const rto_tree* t, int plane, void* host_dst, size_t byt
         case RTO_PLANE_GRID_BRICKS8: src = t->grid_bricks8; have = t->grid_K ? (size_t)t->n_bricks * 512 : 0; break;
         case RTO_PLANE_GRID_LEAF_TOP: src = t->grid_leaf_top; have = t->grid_leaf_top ? ((size_t)1 << (3 * t->grid_K)) * sizeof(uint32_t) : 0; break;
         case RTO_PLANE_GRID_LEAF_BRICKS: src = t->grid_leaf_bricks; have = t->grid_leaf_top ? (size_t)t->n_bricks * 512 * sizeof(uint32_t) : 0; break;
+        case RTO_PLANE_GRID_MARCH_TOP: src = t->grid_top_m; have = t->grid_top_m ? ((size_t)1 << (3 * t->grid_K)) * sizeof(uint32_t) : 0; break;
         default: return fail(RTO_ERR_INVALID, "unknown plane %d", plane);
     }
     if (bytes != have) return fail(RTO_ERR_INVALID, "plane %d holds %zu bytes, caller asked for %zu", plane, have, bytes);
@@ -282,6 +284,7 @@ void rto_tree_destroy(rto_tree* t) {
     cudaFree(t->grid_bricks8);
     cudaFree(t->grid_leaf_top);
     cudaFree(t->grid_leaf_bricks);
+    cudaFree(t->grid_top_m);
     delete t;
 }
 
@@ -427,7 +430,8 @@ static int fill_render_args(rto_context* c, const rto_tree* t, const rto_camera*
     fp.step_size = opt->step_size; fp.sigma_thresh = opt->sigma_thresh; fp.background = opt->background_brightness;
     fp.W = c->W; fp.H = c->H;
     a.tree = rto::TreeDev{t->nodes, t->payload, t->info.payload_stride_halfs, t->info.basis_dim, t->info.max_depth,
-                          rto::make_grid_dev(t->grid_top, t->grid_bricks, t->grid_K, t->grid_bricks8, t->grid_leaf_top, t->grid_leaf_bricks),
+                          rto::make_grid_dev(t->grid_top, t->grid_bricks, t->grid_K, t->grid_bricks8, t->grid_leaf_top, t->grid_leaf_bricks,
+                                             rto::bias_march_table(t->grid_top_m, t->grid_K)),
                           (size_t)t->n_bricks * 512 * sizeof(uint32_t)};
     a.rng_state = c->rng.state; a.rng_inc = c->rng.inc;
     a.x0 = x0; a.y0 = y0; a.x1 = x1; a.y1 = y1;
@@ -738,6 +742,7 @@ struct rto_frame {
     rto::RenderArgs args{};
     void* kparams[1] = {nullptr};
     int launches_per_frame = 0;
+    int64_t pending = -1;   // rto_frame_sequence: index of the frame in flight on this slot (-1: none)
 };
 
 extern "C" {
@@ -836,6 +841,35 @@ int rto_frame_launch_indexed(rto_frame* f, const float c2w[12], int64_t warmup, 
     if (!f) return fail(RTO_ERR_INVALID, "NULL argument");
     if (int rc = rto_context_rng_set_frame(f->ctx, warmup, frame)) return rc;
     return rto_frame_launch(f, c2w, stream);
+}
+
+int rto_frame_sequence(rto_frame* const* frames, void* const* streams, int n_slots, const float* c2w, int64_t n_poses,
+                       int64_t warmup, int64_t first, int64_t count, int drain, rto_frame_retired_fn retired, void* user) {
+    if (!frames || !streams || !c2w || n_slots <= 0 || n_poses <= 0 || first < 0 || count < 0) return fail(RTO_ERR_INVALID, "bad argument");
+    for (int k = 0; k < n_slots; ++k)
+        if (!frames[k]) return fail(RTO_ERR_INVALID, "frames[%d] is NULL", k);
+    auto retire = [&](int k) -> int {   // slot k's previous frame is complete on the host
+        RTO_CUDA(cudaStreamSynchronize((cudaStream_t)streams[k]));
+        rto_frame* f = frames[k];
+        if (f->pending >= 0) {
+            const int64_t done = f->pending;
+            f->pending = -1;
+            if (retired) retired(user, done, k);
+        }
+        return RTO_OK;
+    };
+    for (int64_t i = first; i < first + count; ++i) {
+        const int k = (int)(i % n_slots);
+        if (int rc = retire(k)) return rc;
+        if (int rc = rto_frame_launch_indexed(frames[k], c2w + 12 * (i % n_poses), warmup, i, streams[k])) return rc;
+        frames[k]->pending = i;
+    }
+    if (drain) {
+        // oldest first: the slots after the last one issued
+        for (int j = 1; j <= n_slots; ++j)
+            if (int rc = retire((int)((first + count - 1 + j) % n_slots))) return rc;
+    }
+    return RTO_OK;
 }
 
 void rto_frame_destroy(rto_frame* f) {

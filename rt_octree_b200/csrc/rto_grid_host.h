@@ -93,6 +93,18 @@ inline void build_grid_leaf_host(const int32_t* child, int K, const std::vector<
             }
 }
 
+// march table of the fused-index marcher (rto_ray.cuh FusedIdx / march_top_entry) from the finished top table
+inline void build_march_top_host(const std::vector<uint32_t>& top, int K, std::vector<uint32_t>& top_m) {
+    const uint32_t S = 1u << K;
+    top_m.resize(top.size());
+    for (uint32_t x = 0; x < S; ++x)
+        for (uint32_t y = 0; y < S; ++y)
+            for (uint32_t z = 0; z < S; ++z) {
+                const size_t t = (((size_t)x << K) | y) << K | z;
+                top_m[t] = march_top_entry(top[t], x, y, z);
+            }
+}
+
 // byte plane of the bricks (rto_ray.cuh brick_byte): depth | 0x80 where sigma is non-zero
 inline void grid_bytes_host(const std::vector<uint32_t>& bricks, std::vector<uint8_t>& bricks8) {
     bricks8.resize(bricks.size());

@@ -285,6 +285,14 @@ __global__ void grid_leaf_brick_kernel(const uint32_t* __restrict__ nodes, const
     leaf_bricks[(size_t)blockIdx.x * 512 + c] = out;
 }
 
+// March table of the fused-index marcher (rto_ray.cuh FusedIdx): leaf words as they are, brick ids as biased cell offsets.
+__global__ void grid_march_top_kernel(const uint32_t* __restrict__ top, int K, uint32_t n_cells, uint32_t* __restrict__ top_m) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_cells) return;
+    const uint32_t mask = (1u << K) - 1u;
+    top_m[t] = march_top_entry(top[t], t >> (2 * K), (t >> K) & mask, t & mask);
+}
+
 // --------------------------------------------------------------------------------------------------- host driver
 namespace {
 struct DevBuf {   // frees on scope exit unless released
@@ -423,14 +431,26 @@ static int grid_leaf_build_device(const uint32_t* nodes, TreeBuilt& out, int64_t
         RTO_TRY(cudaGetLastError(), "grid_leaf_brick_kernel");
         ++*launches;
     }
+    // march table (fused-index marcher): needs the leaf-id planes (its collisions are cell references) and brick
+    // offsets below 2^31 - bias; RTO_FUSED_INDEX=0 skips it (the v9 loop then runs)
+    DevBuf tm;
+    const char* fo = getenv("RTO_FUSED_INDEX");
+    const bool fused = out.n_bricks <= RTO_FUSED_MAX_BRICKS && !(fo && fo[0] == '0');
+    if (fused) {
+        RTO_TRY(tm.alloc((size_t)n_cells * sizeof(uint32_t)), "cudaMalloc(grid march table)");
+        grid_march_top_kernel<<<blocks_for(n_cells, 256), 256>>>(out.grid_top, out.grid_K, n_cells, tm.as<uint32_t>());
+        RTO_TRY(cudaGetLastError(), "grid_march_top_kernel");
+        ++*launches;
+    }
     RTO_TRY(cudaDeviceSynchronize(), "grid leaf planes");
     out.grid_leaf_top = lt.release<uint32_t>();
     out.grid_leaf_bricks = lb.release<uint32_t>();
+    if (fused) out.grid_top_m = tm.release<uint32_t>();
     return RTO_OK;
 }
 
 void tree_built_free(TreeBuilt& b) {
-    cudaFree(b.grid_leaf_top); cudaFree(b.grid_leaf_bricks);
+    cudaFree(b.grid_leaf_top); cudaFree(b.grid_leaf_bricks); cudaFree(b.grid_top_m);
     cudaFree(b.nodes); cudaFree(b.payload); cudaFree(b.grid_top); cudaFree(b.grid_bricks); cudaFree(b.grid_bricks8);
     b = TreeBuilt{};
 }

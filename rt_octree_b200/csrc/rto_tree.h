@@ -28,6 +28,7 @@ struct TreeBuilt {   // device planes, owned by the caller after a successful bu
     uint8_t* grid_bricks8 = nullptr;   // byte plane of the bricks (rto_ray.cuh GridDev)
     uint32_t* grid_leaf_top = nullptr;     // leaf-id planes (rto_ray.cuh GridDev::leaf_top / leaf_bricks); nullptr: not built
     uint32_t* grid_leaf_bricks = nullptr;
+    uint32_t* grid_top_m = nullptr;        // march table of the fused-index marcher (rto_ray.cuh FusedIdx); nullptr: not built
     int grid_K = 0;
     int64_t n_bricks = 0;
     int64_t n_leaves = 0;

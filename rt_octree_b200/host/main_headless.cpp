@@ -428,14 +428,37 @@ void run_shard_pipelined(const Job& job, N3Tree& tree, Denoiser& denoiser, size_
         });
     };
     const auto t0 = std::chrono::steady_clock::now();
-    for (size_t i = begin; i < end; ++i) {
-        Slot& s = *slots[(i - begin) % job.pipe];
-        retire(s);
-        { std::unique_lock<std::mutex> l(s.mu); s.cv.wait(l, [&] { return !s.writing; }); }   // pinned buffers free again
-        issue(s, job.trans[i], job.warmup, (int64_t)i);
-        s.pending = (long)i;
+    if (job.graph && end > begin) {
+        // the whole loop is ONE library call (rto_frame_sequence): frame i on slot i % N, the slot's stream waited for before
+        // reuse; the callback hands a finished frame's pinned buffers to a writer and returns when they are free again
+        static_assert(sizeof(Mat43) == 12 * sizeof(float), "poses are passed as a dense [n][12] array");
+        std::vector<rto_frame*> frames;
+        std::vector<void*> streams;
+        for (auto& s : slots) { frames.push_back(s->frame); streams.push_back(s->stream); }
+        struct Retire {
+            decltype(retire)* fn;
+            std::vector<std::unique_ptr<Slot>>* slots;
+        } ctx{&retire, &slots};
+        auto cb = [](void* user, int64_t frame_index, int slot) {
+            Retire& r = *static_cast<Retire*>(user);
+            Slot& s = *(*r.slots)[(size_t)slot];
+            s.pending = (long)frame_index;
+            (*r.fn)(s);
+            std::unique_lock<std::mutex> l(s.mu);
+            s.cv.wait(l, [&] { return !s.writing; });   // pinned buffers free again
+        };
+        rto_check(rto_frame_sequence(frames.data(), streams.data(), job.pipe, job.trans[0].m, (int64_t)job.trans.size(), job.warmup,
+                                     (int64_t)begin, (int64_t)(end - begin), 1, cb, &ctx), "rto_frame_sequence");
+    } else {
+        for (size_t i = begin; i < end; ++i) {
+            Slot& s = *slots[(i - begin) % job.pipe];
+            retire(s);
+            { std::unique_lock<std::mutex> l(s.mu); s.cv.wait(l, [&] { return !s.writing; }); }   // pinned buffers free again
+            issue(s, job.trans[i], job.warmup, (int64_t)i);
+            s.pending = (long)i;
+        }
+        for (auto& s : slots) retire(*s);
     }
-    for (auto& s : slots) retire(*s);
     st.wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();   // results on the host
     for (auto& s : slots) { std::unique_lock<std::mutex> l(s->mu); s->cv.wait(l, [&] { return !s->writing; }); }
     pool.reset();

@@ -69,6 +69,8 @@ def host_ray_lib():
     lib.host_ray_use_byte_bricks.argtypes = [I]
     lib.host_ray_use_deferred_hits.restype = None
     lib.host_ray_use_deferred_hits.argtypes = [I]
+    lib.host_ray_use_fused_index.restype = None
+    lib.host_ray_use_fused_index.argtypes = [I]
     return lib
 
 

@@ -21,7 +21,7 @@ struct HostRay {   // per-ray scratch (shared memory on the GPU: SmemRay in rto_
     float& dst(int i) { return d[i]; }
     uint32_t& hit_leaf(int i) { return hl[i]; }
     float& hit_cnt(int i) { return hc[i]; }
-    float sc[2];
+    float sc[3];
     float& scratch(int i) { return sc[i]; }
 };
 
@@ -46,7 +46,14 @@ void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameP
         auto sink = [&](uint32_t step, uint32_t leaf) {
             if (leaf_seq && (int)step < max_seq) leaf_seq[r * max_seq + step] = (int32_t)leaf;
         };
-        if (grid && grid->bricks8 && grid->leaf_top) {   // production configuration: byte plane + deferred leaf look-up
+        if (grid && grid->bricks8 && grid->leaf_top && grid->top_m) {   // PRODUCTION: fused-index marcher (byte plane, deferred hits)
+            switch (grid->K) {
+#define FK(KK) case KK: walk_grid_fused<SPP, true, KK>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink); \
+                        resolve_hits_fused<SPP, KK>(*grid, mem, wo.n_hits); break;
+                FK(1) FK(2) FK(3) FK(4) FK(5) FK(6) FK(7) FK(8)
+#undef FK
+            }
+        } else if (grid && grid->bricks8 && grid->leaf_top) {   // v9: byte plane + deferred leaf look-up, shift-built indices
             walk_grid<SPP, true, true, true>(nodes, *grid, mem, rs, fp.step_size, fp.sigma_thresh, wo, sink);
             resolve_hits<SPP>(*grid, mem, wo.n_hits);
         } else if (grid && grid->bricks8)
@@ -68,9 +75,10 @@ void run(const uint32_t* nodes, const GridDev* grid, int max_depth, const FrameP
 }
 }  // namespace
 
-static std::vector<uint32_t> g_top, g_bricks, g_leaf_top, g_leaf_bricks;
+static std::vector<uint32_t> g_top, g_bricks, g_leaf_top, g_leaf_bricks, g_top_m;
 static std::vector<uint8_t> g_bricks8;
-static GridDev g_grid{nullptr, nullptr, 0, nullptr, nullptr, nullptr};
+static GridDev g_grid{nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr};
+static bool g_fused = true;
 static bool g_grid_on = false;
 static bool g_byte_bricks = true;
 static bool g_defer = true;
@@ -89,6 +97,12 @@ extern "C" void host_ray_use_deferred_hits(int on) {
     g_grid.leaf_bricks = g_defer && !g_leaf_bricks.empty() ? g_leaf_bricks.data() : nullptr;
 }
 
+// 1 (default): the fused-index marcher (production, needs byte bricks + deferred hits); 0: the v9 shift-built indices
+extern "C" void host_ray_use_fused_index(int on) {
+    g_fused = on != 0;
+    g_grid.top_m = g_fused && !g_top_m.empty() ? bias_march_table(g_top_m.data(), g_grid.K) : nullptr;
+}
+
 // Build (or drop, child == NULL) the sparse brick grid used by subsequent host_ray_walk calls.
 // Returns K (0 = not built for this depth), n_bricks through *n_bricks.
 extern "C" int host_ray_set_grid(const int32_t* child, const uint16_t* data, int data_dim, int64_t capacity, int max_depth,
@@ -100,8 +114,10 @@ extern "C" int host_ray_set_grid(const int32_t* child, const uint16_t* data, int
     if (g_bricks.empty()) g_bricks.assign(512, 0u);
     grid_bytes_host(g_bricks, g_bricks8);
     build_grid_leaf_host(child, K, g_top, g_bricks.size() / 512, g_leaf_top, g_leaf_bricks);
+    build_march_top_host(g_top, K, g_top_m);
     g_grid = make_grid_dev(g_top.data(), g_bricks.data(), K, g_byte_bricks ? g_bricks8.data() : nullptr,
-                           g_defer ? g_leaf_top.data() : nullptr, g_defer ? g_leaf_bricks.data() : nullptr);
+                           g_defer ? g_leaf_top.data() : nullptr, g_defer ? g_leaf_bricks.data() : nullptr,
+                           g_fused ? bias_march_table(g_top_m.data(), K) : nullptr);
     g_grid_on = true;
     if (n_bricks) *n_bricks = (int64_t)(g_bricks.size() / 512);
     return K;

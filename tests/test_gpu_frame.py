@@ -119,3 +119,48 @@ def test_image_target_redirects_the_final_stores(capi, mid_tree, poses8, net_wei
     b.set_image_target(None, None)
     with pytest.raises(capi.RtoError):
         b.set_image_target(None, a.image_rgba8_ptr)
+
+
+def test_frame_sequence_equals_frame_by_frame(capi, mid_tree, poses8, net_weights):
+    """rto_frame_sequence (the pipelined driver's host loop in one library call: slot waits, rng + pose per frame, graph
+    launches) delivers every frame's RGBA8 buffer exactly as a frame-by-frame rto_frame_launch_indexed loop does, reports
+    every frame once, in issue order per slot, before its slot is reused, and drains on request."""
+    W, H, n_slots, n_frames = 200, 152, 3, 11
+    t, cam, opt, net = _rig(capi, mid_tree, W, H, 6, True, net_weights)
+    ctxs = [capi.RenderContext(W, H) for _ in range(n_slots)]
+    bufs = [capi.PinnedBuffer((H, W, 4), np.uint8) for _ in range(n_slots)]
+    streams = [capi.stream_create() for _ in range(n_slots)]
+    frames = [capi.Frame(ctxs[k], t, net, opt, cam.fx, cam.fy, rgba8=bufs[k]) for k in range(n_slots)]
+    got, order = {}, []
+
+    def retired(idx, slot):
+        assert slot == idx % n_slots
+        order.append(idx)
+        got[idx] = bufs[slot].array.copy()
+
+    seq = capi.FrameSequence(frames, streams, poses8, warmup=100, retired=retired)
+    first = 5
+    seq.run(first, 4)                       # frames 5..8: 5 is retired when slot 5 % 3 is reused by frame 8
+    assert order == [5]
+    seq.run(first + 4, n_frames - 4, drain=True)
+    assert sorted(order) == list(range(first, first + n_frames)) and len(order) == n_frames
+    for k in range(n_slots):                # per slot, frames retire in issue order
+        mine = [i for i in order if i % n_slots == k]
+        assert mine == sorted(mine)
+    # frame by frame on one context
+    ref = capi.RenderContext(W, H)
+    b = capi.PinnedBuffer((H, W, 4), np.uint8)
+    fr = capi.Frame(ref, t, net, opt, cam.fx, cam.fy, rgba8=b)
+    for i in range(first, first + n_frames):
+        fr.launch_indexed(poses8[i % len(poses8)], i, 100, streams[0])
+        capi.synchronize(streams[0])
+        assert np.array_equal(got[i], b.array), i
+    assert len({got[i].tobytes() for i in got}) > 1
+    # argument checks
+    with pytest.raises(capi.RtoError):
+        capi.FrameSequence(frames, streams, poses8).run(-1, 2)
+    fr.close()
+    for f in frames:
+        f.close()
+    for st in streams:
+        capi.stream_destroy(st)

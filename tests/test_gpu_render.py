@@ -398,16 +398,19 @@ def test_byte_brick_plane_equals_word_plane(capi, mid_tree, poses8, monkeypatch)
         t, ctx, cam = _setup(capi, tr_, W, H, fx)
         cam.transform = poses8[3]
         out = {}
-        for g8 in ("1", "0", "nodefer"):
+        for g8 in ("1", "0", "nodefer", "nofused"):   # "1" = production: byte plane, deferred hits, fused table indices
             monkeypatch.setenv("RTO_GRID8", "0" if g8 == "0" else "1")
             monkeypatch.setenv("RTO_DEFER_HITS", "0" if g8 == "nodefer" else "1")   # collisions: leaf-id planes vs root descent
+            monkeypatch.setenv("RTO_FUSED_INDEX", "0" if g8 == "nofused" else "1")  # table indices: shift-built (v9) vs fp adder
             ctx.rng_set_frame(3)
             capi.launch_renderer(t, cam, _opts(capi, 6, sigma_thresh=thresh), ctx)
             out[g8] = (ctx.read_aux().copy(), ctx.read_image().copy())
         monkeypatch.delenv("RTO_GRID8")
         monkeypatch.delenv("RTO_DEFER_HITS")
+        monkeypatch.delenv("RTO_FUSED_INDEX")
         assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
         assert np.array_equal(out["1"][0], out["nodefer"][0]) and np.array_equal(out["1"][1], out["nodefer"][1])
+        assert np.array_equal(out["1"][0], out["nofused"][0]) and np.array_equal(out["1"][1], out["nofused"][1])
         assert out["1"][0][3].max() == 1.0
 
 

@@ -53,6 +53,15 @@ def test_planes_and_device_grid_equal_host_builder(capi, depth):
     assert np.array_equal(top_d, top_h), "%d top-table cells differ" % int((top_d != top_h).sum())
     br_d, br_h = t.read_plane("grid_bricks"), h.read_plane("grid_bricks")
     assert np.array_equal(br_d, br_h), "%d brick cells differ" % int((br_d != br_h).sum())
+    # march table of the fused-index marcher (rto_ray.cuh march_top_entry): leaf words unchanged, brick ids as biased offsets
+    K = depth - 3
+    tm = t.read_plane("grid_march_top")
+    cell = np.arange(top_d.size, dtype=np.int64)
+    off = 512 * (cell >> (2 * K)) + 64 * ((cell >> K) & ((1 << K) - 1)) + 8 * (cell & ((1 << K) - 1))
+    leafcell = (top_d & 0x80000000) != 0
+    want = np.where(leafcell, top_d.astype(np.int64), top_d.astype(np.int64) * 512 + (1 << 18) - off)
+    assert np.array_equal(tm.astype(np.int64), want) and not (tm[~leafcell] & 0x80000000).any()
+    assert np.array_equal(tm, h.read_plane("grid_march_top"))
     # every brick cell is a leaf word whose depth field lies in (K, K+3]
     if br_d.size:
         d = ((br_d >> 23) & 0xff).astype(np.int64) - 127

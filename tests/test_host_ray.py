@@ -77,10 +77,10 @@ def test_empty_and_degenerate_trees(oracle, host_ray_lib, poses8):
             assert o["aux"][3].max() == 1.0
 
 
-@pytest.mark.parametrize("byte_bricks,deferred", [(True, True), (True, False), (False, False)],
-                         ids=["bytes+leaf_planes(production)", "bytes", "words"])
+@pytest.mark.parametrize("byte_bricks,deferred,fused", [(True, True, True), (True, True, False), (True, False, False), (False, False, False)],
+                         ids=["fused_index(production)", "bytes+leaf_planes(v9)", "bytes", "words"])
 @pytest.mark.parametrize("spp", [1, 6, 32])
-def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp, byte_bricks, deferred):
+def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp, byte_bricks, deferred, fused):
     """The sparse brick grid walker (rto_ray.cuh walk_grid: 1-2 loads per step, no descent) against the oracle; the VERIFY
     build also checks at every step that the grid's (depth, sigma) equal the tree's, and at every collision that the
     leaf-id plane names the leaf the root descent finds (term == -777 flags a mismatch)."""
@@ -92,7 +92,7 @@ def test_host_grid_walk_bit_exact(oracle, host_ray_lib, mid_tree, poses8, spp, b
         rng = oracle.frame_rng(pi)
         o = oracle.render(mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48)
         h = host_walk(host_ray_lib, mid_tree, poses8[pi], W, H, fx, fx, spp, rng, max_seq=48, grid=True, byte_bricks=byte_bricks,
-                      deferred=deferred)
+                      deferred=deferred, fused=fused)
         assert not (h["term"] == -777).any(), "grid (depth, sigma) disagrees with the tree"
         for k in TRACE_KEYS + ("leaf_seq",):
             assert np.array_equal(h[k], o[k]), (k, spp, pi)
@@ -122,3 +122,29 @@ def test_host_grid_walk_other_depths(oracle, host_ray_lib, poses8):
     assert not (h["term"] == -777).any()
     for k in TRACE_KEYS:
         assert np.array_equal(h[k], o[k]), k
+
+
+def _sphere_sdf(p):
+    return np.sqrt((p.astype(np.float32) ** 2).sum(-1)) - np.float32(0.35)
+
+
+@pytest.mark.parametrize("depth", [5, 7, 8, 9, 10, 11])
+def test_host_fused_index_every_grid_level(oracle, host_ray_lib, poses8, depth):
+    """The fused-index marcher (rto_ray.cuh FusedIdx: per-K magic adds, biased march table, sign trick on the z add for the K
+    whose exponent sum leaves bit 31 clear) on trees of every remaining grid level K = depth - 3 (K = 1, 3 above): all trace
+    fields and the visited-leaf sequence equal the oracle's, the grid agrees with the tree at every step (term != -777), and
+    the v9 loop gives the same record."""
+    from rt_octree_b200 import synthetic as S
+
+    tree = S.make_tree(depth=depth, shell=0.02, halo=0.04 if depth < 10 else 0.01, seed=depth, sdf=_sphere_sdf)
+    W, H, spp = 48, 36, 6
+    fx = S.blender_focal(W)
+    rng = oracle.frame_rng(3)
+    o = oracle.render(tree, poses8[3], W, H, fx, fx, spp, rng, max_seq=32)
+    h = host_walk(host_ray_lib, tree, poses8[3], W, H, fx, fx, spp, rng, max_seq=32, grid=True)
+    v9 = host_walk(host_ray_lib, tree, poses8[3], W, H, fx, fx, spp, rng, max_seq=32, grid=True, fused=False)
+    assert not (h["term"] == -777).any(), "march table disagrees with the tree"
+    for k in TRACE_KEYS + ("leaf_seq",):
+        assert np.array_equal(h[k], o[k]), (k, depth)
+        assert np.array_equal(h[k], v9[k]), (k, depth)
+    assert o["n_hits"].max() >= 1 and o["depth_sum"].max() > 0

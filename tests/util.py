@@ -27,12 +27,14 @@ def tree_depth(tree):
 
 
 def host_walk(lib, tree, c2w12, W, H, fx, fy, spp, rng, ndc=(-1.0, 0.0, 0.0), step_size=1e-4, sigma_thresh=1e-2,
-              thresh=None, max_seq=0, pix_range=None, grid=False, byte_bricks=True, deferred=True):
-    """grid=True: march over the sparse brick grid (walk_grid, VERIFY build) instead of the ancestor-stack walker;
-    byte_bricks selects the plane the marcher reads (byte plane = production, 4-byte leaf words = RTO_GRID8=0)."""
+              thresh=None, max_seq=0, pix_range=None, grid=False, byte_bricks=True, deferred=True, fused=True):
+    """grid=True: march over the sparse brick grid (VERIFY build) instead of the ancestor-stack walker; with the defaults
+    that is the PRODUCTION marcher (walk_grid_fused: byte plane, deferred hits, fused table indices).  fused=False selects
+    the v9 loop (walk_grid), byte_bricks the plane it reads (4-byte leaf words = RTO_GRID8=0), deferred the collision path."""
     nodes = encode_nodes(tree)
     lib.host_ray_use_byte_bricks(1 if byte_bricks else 0)
     lib.host_ray_use_deferred_hits(1 if deferred else 0)   # collisions resolved through the leaf-id planes after the march
+    lib.host_ray_use_fused_index(1 if (fused and byte_bricks and deferred) else 0)
     if grid:
         child = np.ascontiguousarray(tree["child"].reshape(-1), np.int32)
         data = np.ascontiguousarray(tree["data"].reshape(-1)).view(np.uint16)

@@ -65,7 +65,7 @@ struct Cfg {
     static constexpr int OFF_W2 = OFF_W1 + 9 * 512;
     static constexpr int OFF_ZERO = OFF_W2 + 6 * 1024;                      // zero block: must lie ABOVE every operand start address
     static constexpr int OFF_BIAS = OFF_ZERO + 2048;
-    static constexpr int OFF_XCH = OFF_BIAS + 40 * 4;                       // epilogue-2 neighbour exchange: [team][parity][pair][dir][8] floats
+    static constexpr int OFF_XCH = OFF_BIAS + 60 * 4;                       // (biases: 40 floats + the same 40 values as 20 half2) ; epilogue-2 neighbour exchange: [team][parity][pair][dir][8] floats
     static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 2 * 2 * 32;            // mbarriers: c1[N1] | mid[N1] | c2[N2] | weights | input tile
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * N1_TILES + N2_TILES + 2);
     // fp32 input tile as the tensor-map TMA load delivers it: [8 planes][TH+4 rows][SW px].  The box starts at image column
@@ -87,8 +87,8 @@ struct Cfg {
 };
 
 // packed weights in global memory: [w1: 9 taps][32 out][8 in] fp16 |
-// [w2: 3 dy][2 k-steps][2 chunks][32 rows = dx*8 + out (24 used)][8 in] fp16 | b1 [32] fp32 | b2 [8] fp32
-constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 6 * 1024, PK_BYTES = PK_BIAS + 40 * 4;
+// [w2: 3 dy][2 k-steps][2 chunks][32 rows = dx*8 + out (24 used)][8 in] fp16 | b1 [32] fp32 | b2 [8] fp32 | b1 [32] b2 [8] fp16
+constexpr int PK_W1 = 0, PK_W2 = 9 * 512, PK_BIAS = PK_W2 + 6 * 1024, PK_BYTES = PK_BIAS + 60 * 4;
 }  // namespace tc
 
 size_t denoise_tc_packed_bytes() { return tc::PK_BYTES; }
@@ -109,6 +109,9 @@ __global__ void pack_weights_kernel(const NetDev net, unsigned char* __restrict_
     }
     if (tid < 32) bias[tid] = __half2float(net.b1[tid]);
     if (tid < 8) bias[32 + tid] = __half2float(net.b2[tid]);
+    __half* bias_h = reinterpret_cast<__half*>(bias + 40);   // the same biases as fp16 pairs (epilogues add them with HADD2)
+    if (tid < 32) bias_h[tid] = net.b1[tid];
+    if (tid < 8) bias_h[32 + tid] = net.b2[tid];
 }
 
 cudaError_t denoise_tc_pack_weights(const NetDev& net, void* packed_dev, cudaStream_t stream) {
@@ -188,19 +191,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 // two conv outputs -> packed fp16 activations, with the reference's rounding points (rto_internal.h NetDev::fused_bias):
 //   fused = 0 : half(float(half(acc)) + bias) ; fused = 1 : half(acc + bias) ; then relu6 (exact on fp16 values).
-__device__ __forceinline__ uint32_t act_h2(float acc0, float acc1, float b0, float b1, int fused) {
-    float v0, v1;
+// `hi` = the upper clamp as a half2: 6 inside the image, 0 for a position outside it (its activation must read as zero
+// padding for conv2): min(max(h, 0), 0) = 0, so the padding costs no select.
+// fused = 0 in PACKED fp16: half(acc) + bias as ONE half2 add.  The reference path rounds float(half(acc)) + float(bias) to
+// fp16; both operands are fp16 values, the fp32 sum carries 24 >= 2*11 + 2 significant bits, so rounding it to fp16 equals
+// the correctly rounded fp16 sum (double rounding is innocuous for addition at that width) — the same bits as HADD2.
+__device__ __forceinline__ uint32_t act_h2(float acc0, float acc1, float b0, float b1, __half2 b01, int fused,
+                                           __half2 hi = __half2{__half_raw{0x4600}, __half_raw{0x4600}}) {
+    __half2 h;
     if (fused) {
-        v0 = acc0 + b0;
-        v1 = acc1 + b1;
+        h = __floats2half2_rn(acc0 + b0, acc1 + b1);   // .x (low 16 bits) = channel 0
     } else {
-        const __half2 r = __floats2half2_rn(acc0, acc1);
-        const float2 f = __half22float2(r);
-        v0 = f.x + b0;
-        v1 = f.y + b1;
+        h = __hadd2_rn(__floats2half2_rn(acc0, acc1), b01);   // b01 = (b0, b1) as stored: fp16
     }
-    __half2 h = __floats2half2_rn(v0, v1);   // .x (low 16 bits) = v0
-    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
+    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), hi);
     uint32_t u;
     memcpy(&u, &h, 4);
     return u;
@@ -381,6 +385,7 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
         // ---- epilogue 1: +b1, relu6, fp16 -> four 8-channel planes, zero outside the image
         {
             const float* bias = reinterpret_cast<const float*>(smem + C::OFF_BIAS);
+            const __half2* bias_h2 = reinterpret_cast<const __half2*>(bias + 40);
             for (int i = team; i < C::N1_TILES; i += 2) {
                 mbar_wait(bar_c1 + 8 * i, 0);
                 tc_fence_after();
@@ -390,14 +395,14 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
                 const int x = q & (PW - 1), y = q >> 6;
                 const int gx = bx + x - 2, gy = by + y - 2;
                 const bool inside = gx >= 0 && gx < W && gy >= 0 && gy < H;
+                const __half2 hi = __float2half2_rn(inside ? 6.f : 0.f);   // outside the image the activation is conv2's zero padding
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t pk[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int ch = c * 8 + 2 * j;
-                        const uint32_t u = act_h2(__uint_as_float(r[ch]), __uint_as_float(r[ch + 1]), bias[ch], bias[ch + 1], fused_bias);
-                        pk[j] = inside ? u : 0u;
+                        pk[j] = act_h2(__uint_as_float(r[ch]), __uint_as_float(r[ch + 1]), bias[ch], bias[ch + 1], bias_h2[ch >> 1], fused_bias, hi);
                     }
                     *reinterpret_cast<uint4*>(smem + C::OFF_MID + (c * C::MID_PX + q) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
@@ -409,6 +414,7 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
         // ---- epilogue 2: combine the three dx blocks of neighbouring rows, +b2, relu6, fp16 -> float ; softmax / guidance
         {
             const float* bias = reinterpret_cast<const float*>(smem + C::OFF_BIAS) + 32;
+            const __half2* bias_h2 = reinterpret_cast<const __half2*>(smem + C::OFF_BIAS + 40 * 4) + 16;
             float4* xch = reinterpret_cast<float4*>(smem + C::OFF_XCH) + team * 16;   // [parity][pair][dir] x 2 float4
             int it = 0;
             for (int j = team; j < C::N2_TILES; j += 2, ++it) {
@@ -452,7 +458,7 @@ guidance_net_tc_kernel(const __grid_constant__ CUtensorMap aux_map, const unsign
                     for (int c = 0; c < 8; c += 2) {
                         const float acc0 = (lft[c] + __uint_as_float(r[8 + c])) + rgt[c];
                         const float acc1 = (lft[c + 1] + __uint_as_float(r[9 + c])) + rgt[c + 1];
-                        const uint32_t u = act_h2(acc0, acc1, bias[c], bias[c + 1], fused_bias);
+                        const uint32_t u = act_h2(acc0, acc1, bias[c], bias[c + 1], bias_h2[c >> 1], fused_bias);
                         __half2 h;
                         memcpy(&h, &u, 4);
                         const float2 f = __half22float2(h);
@@ -537,12 +543,19 @@ __device__ __forceinline__ void filter_pass1(const float* __restrict__ aux, cons
         const int S = l + 1;
         float e[12];   // E_l = e^{g_l}, already exponentiated by the GuidanceNet epilogue; load12 yields 0 outside the image
         load12<GUARD>(guidance + l * HW, W, vec, rowin, rowoff, xs, e);
+        // the four windows [R+j-S, R+j+S], j = 0..3, share the core [R+3-S, R+S] (2S-2 taps, none for S = 1): it is summed
+        // once and every output adds its own three taps — 8S+40 instead of 32S+16 operations per level
+        float4 core = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = R + 3 - S; i <= R + S; ++i) {
+            core.x = fmaf(e[i], cr[i], core.x); core.y = fmaf(e[i], cg[i], core.y); core.z = fmaf(e[i], cb[i], core.z); core.w += e[i];
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a = core;
 #pragma unroll
-            for (int dx = -S; dx <= S; ++dx) {
-                const int i = R + j + dx;
+            for (int i = R + j - S; i <= R + j + S; ++i) {
+                if (i >= R + 3 - S && i <= R + S) continue;   // core tap (compile-time after unrolling)
                 a.x = fmaf(e[i], cr[i], a.x); a.y = fmaf(e[i], cg[i], a.y); a.z = fmaf(e[i], cb[i], a.z); a.w += e[i];
             }
             Hs[(l * SROWS + r) * BW + 4 * xg + (j ^ sw)] = a;   // swizzle: conflict-free 16-byte stores
@@ -574,11 +587,19 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const int S = l + 1;
+            // the three row windows [k-S, k+S], k = 0..2, share the core rows [2-S, S]: summed once, then two rows each
             float4 acc[3];
+            float4 core = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int rr = 2 - S; rr <= S; ++rr) {
+                const float4 v = Hs[(l * SROWS + ty + R + rr) * BW + slot];
+                core.x += v.x; core.y += v.y; core.z += v.z; core.w += v.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[k] = core;
 #pragma unroll
             for (int rr = -S; rr <= 2 + S; ++rr) {
+                if (rr >= 2 - S && rr <= S) continue;   // core row
                 const float4 v = Hs[(l * SROWS + ty + R + rr) * BW + slot];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)

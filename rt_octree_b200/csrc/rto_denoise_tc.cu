@@ -570,7 +570,10 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
     extern __shared__ __align__(16) unsigned char fsm[];
     float4* Hs = reinterpret_cast<float4*>(fsm);                  // [4][SROWS][BW], columns swizzled inside groups of 4
     const int tid = threadIdx.x;
-    const int bx = blockIdx.x * BW, by = y0 + blockIdx.y * BH;
+    // Block rows are anchored at ABSOLUTE image rows (multiples of BH), not at the band start: the shared-core sums below add a
+    // pixel's window rows in an order that depends on its place in the 3-row group, and a pixel must get the same bits whether
+    // it is produced by a full-frame launch or by a band of the tile split.
+    const int bx = blockIdx.x * BW, by = (y0 / BH + blockIdx.y) * BH;
     const size_t HW = (size_t)W * H;
     const bool interior = (W & 3) == 0 && bx >= R && bx + BW + R <= W && by >= R && by + BH + R <= H &&
                           (reinterpret_cast<uintptr_t>(aux) & 15) == 0 && (reinterpret_cast<uintptr_t>(guidance) & 15) == 0;
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int gy = by + ty + k;
-                if (gx < W && gy < H && gy < y1) {
+                if (gx < W && gy < H && gy >= y0 && gy < y1) {
                     const float w = __fdividef(RTO_LD_LAST(weight + l * HW + (size_t)gy * W + gx), acc[k].w);
                     o[k][0] += acc[k].x * w; o[k][1] += acc[k].y * w; o[k][2] += acc[k].z * w;
                 }
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(fs::THREADS, 3) filter_sep_kernel(const float*
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int gy = by + ty + k;
-            if (gx < W && gy < H && gy < y1) {
+            if (gx < W && gy < H && gy >= y0 && gy < y1) {
                 RTO_ST(out + (size_t)gy * W + gx, make_float4(o[k][0], o[k][1], o[k][2], 1.0f));
                 if (out8) RTO_ST(out8 + (size_t)gy * W + gx, rgba8_of(o[k][0], o[k][1], o[k][2], 1.0f));   // the bytes `-o` writes to the PNG
             }
@@ -720,7 +723,7 @@ cudaError_t launch_filter_fast(const float* aux, const float* weight, const floa
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    dim3 grid((W + fs::BW - 1) / fs::BW, (rows + fs::BH - 1) / fs::BH);
+    dim3 grid((W + fs::BW - 1) / fs::BW, (y1 + fs::BH - 1) / fs::BH - y0 / fs::BH);   // block rows anchored at multiples of BH (see the kernel)
     filter_sep_kernel<<<grid, fs::THREADS, fs::SMEM_BYTES, stream>>>(aux, weight, guidance, W, H, y0, y1, out, out8);
     return cudaGetLastError();
 }

@@ -21,7 +21,11 @@ cuobjdump -sass "$LIB" > "$TMP"
   echo "## guidance_net_tc_kernel<10>: every UTMALDG / UTCHMMA / UTCBAR / LDTM / UBLKCP / UTCATOMSWS line (address, instruction)"
   awk '/Function : .*guidance_net_tc_kernelILi10E/{p=1; next} /Function : /{p=0} p && /UTMALDG|UTCHMMA|LDTM|UBLKCP|UTCBAR|UTCATOMSWS/ && !/^\s*\/\* 0x/{print}' "$TMP" | sed 's/ *\/\* 0x[0-9a-f]* \*\/ *$//' | head -80
   echo
-  echo "## render_kernel<6,false,3> (production): the marching loop, from the FFMA.SAT position update to the loop branch"
+  echo "## render_kernel<6,false,16> (production: fused-index marcher, grid level K = 6 = the bench tree): the marching loop,"
+  echo "## from the FFMA.SAT position update to the loop branch"
+  awk '/Function : _ZN3rto13render_kernelILi6ELb0ELi16EEE/{p=1; next} /Function : /{p=0} p' "$TMP" | grep -v '^\s*/\* 0x' | sed 's/ *\/\* 0x[0-9a-f]* \*\/ *$//' | awk '/FFMA.SAT/ && !s {s=1} s{print} s && /BSYNC.RECONVERGENT B1/{exit}'
+  echo
+  echo "## render_kernel<6,false,3> (v9 loop, RTO_FUSED_INDEX=0): the same span, for comparison"
   awk '/Function : _ZN3rto13render_kernelILi6ELb0ELi3EEE/{p=1; next} /Function : /{p=0} p' "$TMP" | grep -v '^\s*/\* 0x' | sed 's/ *\/\* 0x[0-9a-f]* \*\/ *$//' | awk '/FFMA.SAT/ && !s {s=1} s{print} s && /BRA P1/{exit}'
 } > "$OUT"
 rm -f "$TMP"

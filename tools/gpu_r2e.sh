@@ -3,8 +3,8 @@
 cd "$(dirname "$0")/.."
 N=${1:-2}; K=${2:-20}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_cli.py tests/test_sharding.py -m gpu -q --tb=short -p no:cacheprovider -k "sharding or tile_split or peer" > gpurun_out/pytest_multi_$N.log 2>&1
-tail -3 gpurun_out/pytest_multi_$N.log
+[ "${3:-tests}" = notests ] || timeout 600 python -m pytest tests/test_cli.py tests/test_sharding.py -m gpu -q --tb=short -p no:cacheprovider -k "sharding or tile_split or peer" > gpurun_out/pytest_multi_$N.log 2>&1
+[ "${3:-tests}" = notests ] || tail -3 gpurun_out/pytest_multi_$N.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps $K --warmup 3 --no-baselines > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err
 echo "bench exit $?"
 python - <<PY

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for compute-sanitizer: the device tree loader (dense + quantised, structure check, grid build, plane
-read-back) and the marching kernel over both brick planes.  Run by tools/gpu_sanitize.sh."""
+read-back) and the marching kernel in its three forms (fused index, v9 loop, word plane).  Run by tools/gpu_sanitize.sh."""
 import os
 import sys
 
@@ -30,13 +30,15 @@ def main():
             t.read_plane(name)
         ctx = capi.RenderContext(W, H)
         out = []
-        for g8 in ("1", "0"):
-            os.environ["RTO_GRID8"] = g8
+        # production (fused-index marcher over the march table + byte plane), the v9 loop, the word plane
+        for env in ({}, {"RTO_FUSED_INDEX": "0"}, {"RTO_GRID8": "0"}):
+            os.environ.update(env)
             ctx.rng_set_frame(2)
             capi.launch_renderer(t, cam, opt, ctx)
             out.append(ctx.read_aux().copy())
-        del os.environ["RTO_GRID8"]
-        assert np.array_equal(out[0], out[1]) and out[0][3].max() == 1.0
+            for k in env:
+                del os.environ[k]
+        assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2]) and out[0][3].max() == 1.0
         ctx.close()
         t.close()
     print("sanitize_tree OK")

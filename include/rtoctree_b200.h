@@ -169,6 +169,12 @@ int rto_context_read_image_rgba8(rto_context* ctx, unsigned char* host_dst, void
  * the image (rto_render with denoise off, rto_denoise's filter) write it from the same epilogue, so the read-back above
  * costs no extra launch. */
 unsigned char* rto_context_image_rgba8(rto_context* ctx);
+/* rows [y0, y1) of that RGBA8 copy into the SAME rows of a full-frame host buffer ([H][W][4] u8): the read-back of one band of a
+ * tile split whose GPUs each deliver their own rows to the host (N PCIe links in parallel) instead of assembling the frame on
+ * one GPU first.  The rows must have been produced on this context (rto_render_rect with denoise off, or rto_denoise_rows)
+ * after rto_context_image_rgba8 created the copy, with no image target set. */
+int rto_context_read_rows_rgba8(rto_context* ctx, unsigned char* host_frame, int y0, int y1, void* stream);
+int rto_context_read_image_rows(rto_context* ctx, float* host_frame, int y0, int y1, void* stream);   /* the same for the float4 image */
 
 /* ---- render : volrend::launch_renderer(tree, cam, options, ctx, stream, offscreen=true)
  *               include/volrend/cuda/renderer_kernel.hpp:11-16, src/cuda/volrend.cu:236-285 ----

@@ -66,7 +66,7 @@ EXPORTS = [  # every symbol include/rtoctree_b200.h declares (tests/test_abi.py 
     "rto_context_read_image", "rto_render", "rto_render_rect", "rto_render_trace",
     "rto_net_create", "rto_net_destroy", "rto_net_set_impl", "rto_net_set_bias_mode", "rto_denoise", "rto_denoise_rows", "rto_net_forward",
     "rto_filter", "rto_filter_forward_save", "rto_filter_backward", "rto_timer_enable", "rto_timer_reset", "rto_timer_record", "rto_timer_report", "rto_launch_count",
-    "rto_context_image_rgba8", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
+    "rto_context_image_rgba8", "rto_context_read_rows_rgba8", "rto_context_read_image_rows", "rto_stream_create", "rto_stream_destroy", "rto_host_alloc", "rto_host_free",
     "rto_frame_create", "rto_frame_launch", "rto_frame_launch_indexed", "rto_frame_sequence", "rto_frame_destroy",
     "rto_context_set_image_target", "rto_context_mark_image_written", "rto_peer_enable", "rto_ipc_export", "rto_ipc_open",
     "rto_ipc_close", "rto_event_create", "rto_event_create_timed", "rto_event_elapsed_ms", "rto_event_record", "rto_stream_wait_event",
@@ -115,6 +115,8 @@ def load(path: str = LIB_PATH):
     L.rto_context_write_aux.argtypes = [P, P, P]
     L.rto_context_read_image_rgba8.argtypes = [P, P, P]
     L.rto_context_read_image.argtypes = [P, P, P]
+    L.rto_context_read_rows_rgba8.argtypes = [P, P, I, I, P]
+    L.rto_context_read_image_rows.argtypes = [P, P, I, I, P]
     L.rto_render.argtypes = [P, P, C.POINTER(CameraPOD), C.POINTER(RenderOptionsPOD), P]
     L.rto_render_rect.argtypes = [P, P, C.POINTER(CameraPOD), C.POINTER(RenderOptionsPOD), I, I, I, I, P]
     L.rto_render_trace.argtypes = [P, P, C.POINTER(CameraPOD), C.POINTER(RenderOptionsPOD), C.POINTER(TracePOD), P]
@@ -439,6 +441,16 @@ class RenderContext:
         if sync:
             _cuda_sync()
         return host
+
+    def read_rows(self, host8=None, host_image=None, rows=(0, 0), stream=0, sync=True):
+        """Rows [y0, y1) of the RGBA8 copy / the float4 image into the same rows of full-frame host arrays (the band
+        read-back of a tile split whose GPUs deliver their own rows: rto_context_read_rows_rgba8 / _read_image_rows)."""
+        if host8 is not None:
+            _check(load().rto_context_read_rows_rgba8(self._h, host8.ctypes.data, int(rows[0]), int(rows[1]), C.c_void_p(stream)))
+        if host_image is not None:
+            _check(load().rto_context_read_image_rows(self._h, host_image.ctypes.data, int(rows[0]), int(rows[1]), C.c_void_p(stream)))
+        if sync:
+            _cuda_sync()
 
     def write_aux(self, host: np.ndarray, stream=0, sync=True):
         """Upload a stored guidance buffer (fp32 [8][H][W], the `buf_*.bin` layout)."""

@@ -391,6 +391,24 @@ int rto_context_read_image_rgba8(rto_context* c, unsigned char* dst, void* strea
     RTO_CUDA(cudaMemcpyAsync(dst, c->img8, (size_t)c->W * c->H * sizeof(uchar4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return RTO_OK;
 }
+int rto_context_read_rows_rgba8(rto_context* c, unsigned char* dst, int y0, int y1, void* stream) {
+    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    if (y0 < 0 || y1 > c->H || y0 >= y1) return fail(RTO_ERR_INVALID, "bad row range [%d, %d) for height %d", y0, y1, c->H);
+    if (!c->img8) return fail(RTO_ERR_INVALID, "no RGBA8 copy on this context: call rto_context_image_rgba8 before producing the rows");
+    if (c->img_target) return fail(RTO_ERR_INVALID, "an image target is set: the rows were stored there, not on this context");
+    const size_t off = (size_t)y0 * c->W;
+    RTO_CUDA(cudaMemcpyAsync(dst + off * sizeof(uchar4), c->img8 + off, (size_t)(y1 - y0) * c->W * sizeof(uchar4), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    return RTO_OK;
+}
+int rto_context_read_image_rows(rto_context* c, float* dst, int y0, int y1, void* stream) {
+    if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
+    if (y0 < 0 || y1 > c->H || y0 >= y1) return fail(RTO_ERR_INVALID, "bad row range [%d, %d) for height %d", y0, y1, c->H);
+    if (c->img_target) return fail(RTO_ERR_INVALID, "an image target is set: the rows were stored there, not on this context");
+    const size_t off = (size_t)y0 * c->W;
+    RTO_CUDA(cudaMemcpyAsync(dst + off * 4, c->img + off, (size_t)(y1 - y0) * c->W * sizeof(float4), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RTO_OK;
+}
 unsigned char* rto_context_image_rgba8(rto_context* c) {
     if (!c || ensure_img8(c) != RTO_OK) return nullptr;
     return reinterpret_cast<unsigned char*>(c->img8);

@@ -60,7 +60,7 @@ struct Args {
 Args parse_args(int argc, char** argv) {
     static const std::map<std::string, std::string> shorts = {{"w", "width"}, {"h", "height"}, {"s", "step_size"}, {"e", "stop_thresh"},
                                                               {"a", "sigma_thresh"}, {"o", "write_images"}, {"i", "intrin"}, {"r", "reverse_yz"}};
-    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float", "no_graph", "tile_split"};
+    static const std::set<std::string> flags = {"reverse_yz", "write_buffer", "help", "dry_run", "write_float", "no_graph", "tile_split", "band_readback"};
     Args a;
     for (int k = 1; k < argc; ++k) {
         std::string t = argv[k];
@@ -110,6 +110,8 @@ void print_help() {
          "      --gpu_list arg      comma-separated device ids, one shard per entry (e.g. 0,1,2,3; 0,0 = two shards on GPU 0)\n"
          "      --tile_split        single-frame latency mode: every frame is cut into row bands over the GPUs of --num_gpus /\n"
          "                          --gpu_list; each band's filter stores into GPU 0's image over NVLink (no gather)\n"
+         "      --band_readback     with --tile_split: every GPU copies its own band to the host frame (N PCIe links in parallel)\n"
+         "                          instead of storing it into the first GPU's image and copying the assembled frame from there\n"
          "      --pipe arg          frames in flight per GPU: N contexts/streams, CUDA-graph frames (default: 1 = reference protocol)\n"
          "      --no_graph          with --pipe: issue the kernels separately instead of one graph launch per frame\n"
          "      --readback arg      copy rgba8 | float | aux to pinned host memory every frame even without -o\n"
@@ -284,7 +286,7 @@ struct Job {
     RenderOptions options;
     int width, height;
     float fx, fy;
-    bool llff, write_buffer, write_float, graph, tile_split;
+    bool llff, write_buffer, write_float, graph, tile_split, band_readback;
     int warmup, pipe, writers;
 };
 
@@ -523,6 +525,10 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
     std::atomic<bool> failed{false};
     float* dst_img = nullptr;          // GPU 0's image / RGBA8 copy: the destination of every band
     unsigned char* dst_img8 = nullptr;
+    // --band_readback: the bands never meet on a GPU; every thread copies its own rows into the shared pinned host frame
+    const bool direct = job.band_readback;
+    uint8_t* host8 = nullptr;          // the first thread's pinned frame(s), written by every thread in that mode
+    float* host_img = nullptr;
     int levels = 4;
     std::vector<double> lat_ms, dev_ms;
     std::vector<int> bounds(n + 1);                  // band g = rows [bounds[g], bounds[g+1]); equal heights to start with
@@ -554,9 +560,11 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
                 levels = denoiser.levels();
                 rto_check(rto_host_alloc(reinterpret_cast<void**>(&h8), px * 4), "pinned rgba8");
                 if (job.write_float) rto_check(rto_host_alloc(reinterpret_cast<void**>(&himg), px * 16), "pinned image");
+                host8 = h8; host_img = himg;
             }
+            if (direct && !rto_context_image_rgba8(ctx.handle)) throw std::runtime_error(rto_last_error());   // the producing kernels write RGBA8 too
             bar.wait();   // destination pointers published
-            if (g != 0) {
+            if (g != 0 && !direct) {
                 rto_check(rto_peer_enable(devices[0]), "peer access to the first GPU");
                 rto_check(rto_context_set_image_target(ctx.handle, dst_img, dst_img8), "image target");
             }
@@ -574,6 +582,24 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
                 rto_check(rto_render_rect(ctx.handle, tree.device, &cam, &opt, 0, r0, W, r1, stream), "render band");
                 if (job.options.denoise) rto_check(rto_denoise_rows(ctx.handle, denoiser.handle(), b0, b1, stream), "denoise band");
                 rto_check(rto_event_record(ev_t1, stream), "event");
+                if (direct) {
+                    // this band's rows go to the host over this GPU's own PCIe link; the frame is complete when every thread is here
+                    rto_check(rto_context_read_rows_rgba8(ctx.handle, host8, b0, b1, stream), "read band rgba8");
+                    if (host_img) rto_check(rto_context_read_image_rows(ctx.handle, host_img, b0, b1, stream), "read band image");
+                    rto_check(rto_synchronize(stream), "sync");
+                    bar.wait();
+                    if (g == 0) {
+                        if (timed) lat_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                        if (timed && job.out_dir.size()) write_outputs(job, out_index, nullptr, h8, himg);
+                    }
+                    rto_check(rto_event_elapsed_ms(ev_t0, ev_t1, &band_ms[g]), "band time");
+                    bar.wait();
+                    if (g == 0) {
+                        if (timed) dev_ms.push_back(*std::max_element(band_ms.begin(), band_ms.end()));
+                        if (balance) bounds = rebalance_bands(bounds, band_ms, H);
+                    }
+                    return;
+                }
                 rto_check(rto_event_record(events[g], stream), "event");
                 bar.wait();   // every band's completion event has been recorded
                 if (g == 0) {
@@ -598,7 +624,7 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
             for (int w = 0; w < job.warmup; ++w) one(job.trans[0], 0, w, false, 0);
             for (size_t i = 0; i < frames; ++i) one(job.trans[i], job.warmup, (int64_t)i, true, i);
             bar.wait();
-            if (g != 0) rto_context_set_image_target(ctx.handle, nullptr, nullptr);
+            if (g != 0 && !direct) rto_context_set_image_target(ctx.handle, nullptr, nullptr);
             rto_host_free(h8); rto_host_free(himg); rto_host_free(haux);
             rto_event_destroy(events[g]);
             rto_event_destroy(ev_t0); rto_event_destroy(ev_t1);
@@ -621,7 +647,8 @@ void run_tile_split(const Job& job, const std::vector<int>& devices) {
     mean /= (double)lat_ms.size();
     printf("tile split: %d bands over GPUs [", n);
     for (int g = 0; g < n; ++g) printf("%s%d", g ? "," : "", devices[g]);
-    printf("], %dx%d, halo %d rows, peer-direct stores into the first GPU\n", W, H, job.options.denoise ? 2 + levels : 0);
+    printf("], %dx%d, halo %d rows, %s\n", W, H, job.options.denoise ? 2 + levels : 0,
+           direct ? "every GPU copies its own band to the host frame" : "peer-direct stores into the first GPU");
     printf("latency: median %.6f ms, mean %.6f ms, min %.6f ms per frame (rendezvous -> RGBA8 frame on the host, %zu frames)\n",
            s[s.size() / 2], mean, s.front(), lat_ms.size());
     std::vector<double> d = dev_ms;
@@ -848,6 +875,7 @@ static int run_main(int argc, char* argv[]) {
     job.writers = args.i("writers", 4);
     job.readback = args.str("readback");
     job.tile_split = args.has("tile_split");
+    job.band_readback = args.has("band_readback");
     if (job.tile_split && job.write_buffer) {
         fprintf(stderr, "ERROR: --tile_split assembles the final image only; --write_buffer needs the frame-sharded modes\n");
         return 1;

@@ -453,10 +453,12 @@ def test_cli_tile_split_matches_full_frame(cli, tmp_path, mid_tree, net_weights,
     a = str(tmp_path / "serial")
     r = subprocess.run([cli, *common, "-o", a], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
-    runs = {"list000": ["--gpu_list", "0,0,0"], "list00": ["--gpu_list", "0,0"]}
+    # --band_readback: no assembly on a GPU, every shard copies its own rows into the host frame
+    runs = {"list000": ["--gpu_list", "0,0,0"], "list00": ["--gpu_list", "0,0"], "band000": ["--gpu_list", "0,0,0", "--band_readback"]}
     n = capi.device_count()
     if n >= 2:
         runs["multi"] = ["--num_gpus", str(min(n, 8))]
+        runs["multi_band"] = ["--num_gpus", str(min(n, 8)), "--band_readback"]
     names = ["img_r_%d.bin" % i for i in range(4)] + ["r_%d.png" % i for i in range(4)]
     for k, extra in runs.items():
         b = str(tmp_path / k)

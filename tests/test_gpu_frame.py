@@ -116,9 +116,28 @@ def test_image_target_redirects_the_final_stores(capi, mid_tree, poses8, net_wei
     assert np.array_equal(a.read_image(), want) and np.array_equal(a.read_image_rgba8(), want8)
     assert capi.launch_count() == n0
     assert np.all(b.read_image()[77:] == 0)           # the second context's own image was not touched
+    # the rows were stored into `a`: a band read-back from `b` must refuse
+    with pytest.raises(capi.RtoError, match="image target"):
+        b.read_rows(host8=np.empty((H, W, 4), np.uint8), rows=(77, H))
     b.set_image_target(None, None)
     with pytest.raises(capi.RtoError):
         b.set_image_target(None, a.image_rgba8_ptr)
+    # the other way to deliver a split frame: no assembly on a GPU, every context copies its own rows into ONE host frame
+    # (rto_context_read_rows_rgba8 / rto_context_read_image_rows)
+    c0, c1 = capi.RenderContext(W, H), capi.RenderContext(W, H)
+    host8, host_img = capi.PinnedBuffer((H, W, 4), np.uint8), capi.PinnedBuffer((H, W, 4), np.float32)
+    with pytest.raises(capi.RtoError, match="RGBA8"):
+        c0.read_rows(host8=host8.array, rows=(0, 10))     # no RGBA8 copy yet
+    for c, band in ((c0, (0, 77)), (c1, (77, H))):
+        assert c.image_rgba8_ptr                           # from now on the filter epilogue writes the RGBA8 rows too
+        c.rng_set_frame(6)
+        y0, y1 = SH.render_rows_for_band(band, H, True, net.levels)
+        capi.launch_renderer(t, cam, opt, c, rect=(0, y0, W, y1))
+        net.denoise(cam, c, rows=band)
+        c.read_rows(host8=host8.array, host_image=host_img.array, rows=band)
+    assert np.array_equal(host8.array, want8) and np.array_equal(host_img.array, want)
+    with pytest.raises(capi.RtoError, match="row range"):
+        c0.read_rows(host8=host8.array, rows=(10, H + 1))
 
 
 def test_frame_sequence_equals_frame_by_frame(capi, mid_tree, poses8, net_weights):

@@ -641,17 +641,18 @@ def run_cuda_arm(args):
         achieved = bytes_frame / (render_ms * 1e-3) / 1e9
         fps = world * 1e3 / ms_per_frame
         fps_protocol = world * 1e3 / (render_ms + net_ms + filter_ms)
-        cfg = base_config(world, K)
-        cfg.update({"streams": n_pipe, "tree_built": dict(nodes=int(info.capacity), leaves=int(info.n_leaves), max_depth=int(info.max_depth),
+        cfg = base_config(world, K)    # identical to the reference arm's `config` (same workload, same keys)
+        run_info = {"streams": n_pipe, "tree_built": dict(nodes=int(info.capacity), leaves=int(info.n_leaves), max_depth=int(info.max_depth),
                                                           node_bytes=int(info.node_bytes), payload_bytes=int(info.payload_bytes),
                                                           grid_bytes=int(info.grid_bytes)),
-                    "tree_load_s": rig.load_s, "min_seconds_per_measurement": min_s})
+                    "tree_load_s": rig.load_s, "min_seconds_per_measurement": min_s}
         line = {
             "metric": "fps_800x800_spp6_denoise", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_frame, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 traversal/shade, f16 GuidanceNet", "data": "synthetic",
             "reps": pl["reps"], "timed_region_s": pl["ms_total"] * 1e-3,
             "config": cfg,
+            "run_info": run_info,
             "value_protocol": "%d frames in flight on %d (context, stream) pairs, %s, device-timed over reps x steps frames"
                               % (n_pipe, n_pipe, "three launches per frame" if args.no_graph else "one rto_frame graph launch per frame"),
             "value_reference_protocol": fps_protocol,

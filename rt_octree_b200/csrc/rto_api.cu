@@ -394,8 +394,8 @@ int rto_context_read_image_rgba8(rto_context* c, unsigned char* dst, void* strea
 int rto_context_read_rows_rgba8(rto_context* c, unsigned char* dst, int y0, int y1, void* stream) {
     if (!c || !dst) return fail(RTO_ERR_INVALID, "NULL argument");
     if (y0 < 0 || y1 > c->H || y0 >= y1) return fail(RTO_ERR_INVALID, "bad row range [%d, %d) for height %d", y0, y1, c->H);
-    if (!c->img8) return fail(RTO_ERR_INVALID, "no RGBA8 copy on this context: call rto_context_image_rgba8 before producing the rows");
     if (c->img_target) return fail(RTO_ERR_INVALID, "an image target is set: the rows were stored there, not on this context");
+    if (!c->img8) return fail(RTO_ERR_INVALID, "no RGBA8 copy on this context: call rto_context_image_rgba8 before producing the rows");
     const size_t off = (size_t)y0 * c->W;
     RTO_CUDA(cudaMemcpyAsync(dst + off * sizeof(uchar4), c->img8 + off, (size_t)(y1 - y0) * c->W * sizeof(uchar4), cudaMemcpyDeviceToHost,
                              (cudaStream_t)stream));

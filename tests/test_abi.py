@@ -57,6 +57,15 @@ def test_argument_validation_without_gpu(capi):
     assert lib.rto_tree_create_quantized(*q(nq=8, nr=1)) == capi.RTO_ERR_INVALID   # retained basis without its array
     assert lib.rto_tree_read_plane(None, 0, data.ctypes.data, 0) == capi.RTO_ERR_INVALID
     assert lib.rto_context_create(C.byref(h), 0, 10) == capi.RTO_ERR_INVALID
+    # pipelined-caller and band read-back entry points validate before touching the device
+    nofn = capi.FRAME_RETIRED_FN(0)
+    assert lib.rto_frame_sequence(None, None, 0, None, 0, 0, 0, 0, 0, nofn, None) == capi.RTO_ERR_INVALID
+    slots = (C.c_void_p * 2)(None, None)
+    poses = np.zeros((1, 12), np.float32)
+    assert lib.rto_frame_sequence(slots, slots, 2, poses.ctypes.data, 1, 100, 0, 1, 0, nofn, None) == capi.RTO_ERR_INVALID
+    assert b"frames[0] is NULL" in lib.rto_last_error()
+    assert lib.rto_context_read_rows_rgba8(None, data.ctypes.data, 0, 1, None) == capi.RTO_ERR_INVALID
+    assert lib.rto_context_read_image_rows(None, data.ctypes.data, 0, 1, None) == capi.RTO_ERR_INVALID
     w = np.zeros(4096, np.float16)
     assert lib.rto_net_create(C.byref(h), w.ctypes.data, w.ctypes.data, w.ctypes.data, w.ctypes.data, 8, 32, 7) == capi.RTO_ERR_UNSUPPORTED
     assert b"Kernel size == 15 not supported" in lib.rto_last_error()   # filtering.cu:362-366 message

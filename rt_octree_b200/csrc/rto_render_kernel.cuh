@@ -42,8 +42,12 @@ constexpr int kTileW = RTO_TILE_W, kTileH = RTO_TILE_H;      // pixels per warp-
 constexpr int kBlockWarps = RTO_BLOCK_WARPS;
 constexpr int kSuperX = kBlockWarps / 2, kSuperY = 2;   // warp tiles per super-tile in x / y
 constexpr int kBlockThreads = 32 * kBlockWarps;
-constexpr int kDefaultBlocksPerSM = 40 / kBlockWarps;      // tuned on B200, 4 frames in flight: 8 blocks (64 regs) 5100, 10 (48 regs) 5280,
-                                                           // 12 (40 regs, spills) 5275 frames/s; single stream 0.2413 / 0.2468 / 0.2683 ms
+constexpr int kDefaultBlocksPerSM = 32 / kBlockWarps;      // RESIDENT blocks per SM (the build keeps 48 registers = an occupancy limit of 10).
+                                                           // Tuned on B200 with the v10 loop (profiles/r02_ab_blocks_per_sm_v10*.json), single
+                                                           // stream ms | 4 frames in flight: 10 blocks 0.1979 | 6580, 9: 0.1931 | 6590,
+                                                           // 8: 0.1927 | 6655, 7: 0.2049 | 6685, 6: 0.2248 | 6656; 8 blocks of a 64-register
+                                                           // build: 0.1910 | 6257 (its CTAs keep the neighbouring frames' kernels off the SM).
+                                                           // (v6 loop, round 1: 8 blocks / 64 regs 5100, 10 / 48 regs 5280, 12 / 40 regs 5275.)
 
 // Per-ray scratch in shared memory, word w of thread t at base[w * kBlockThreads + t] (conflict-free):
 //   [0, D]            ancestor stack (D = tree max depth)

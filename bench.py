@@ -512,7 +512,8 @@ def run_cuda_arm(args):
     t_clk0 = clocks.mark()
     pl = rig.pipelined(my_frames, n_pipe, Wm, min_s, barrier, graph=not args.no_graph)
     t_clk1 = clocks.mark()
-    barrier()
+    clk = clocks.stop(t_clk0, t_clk1) if rank == 0 else None   # the sampler covers the timed region of `value` and is gone before
+    barrier()                                                   # the host-side (e2e) measurements: nvidia-smi polling takes driver locks
     sp = rig.serial_protocol(my_frames, min_s)
 
     # ---- cold-L2 variant: flush L2 (256 MB write) before every frame, per-frame events
@@ -533,7 +534,6 @@ def run_cuda_arm(args):
     e8 = rig.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph)
     e8py = rig.e2e(my_frames, NSLOT, "rgba8", Wm, min_s, barrier, graph=not args.no_graph, sequence=False)
     ef = rig.e2e(my_frames, max(args.pipe, 3), "float", Wm, min_s, barrier, graph=not args.no_graph)
-    clk = clocks.stop(t_clk0, t_clk1) if rank == 0 else None
 
     ms_per_frame, e2e8_ms, e2ef_ms, cold_ms, render_ms, net_ms, filter_ms, e2e8py_ms = reduce_max(
         [pl["ms_total"] / (pl["reps"] * K), 1e3 * e8["seconds"] / e8["frames"], 1e3 * ef["seconds"] / ef["frames"], cold_ms,

@@ -391,6 +391,23 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem)) != cudaSuccess) return e;
         ds.occ_limit[v] = occ > 0 ? occ : 1;
         ds.smem_set[v] = smem;
+        // Shared-memory carve-out.  The driver sizes it for the kernel's OCCUPANCY LIMIT (10 blocks), but the launch keeps fewer
+        // blocks resident (tuned_blocks_per_sm): ask for what those need — per block the dynamic scratch + the static word +
+        // the 1 KB the system reserves — so that the rest of the 256 KB stays L1 for the brick planes.  A hint, rounded up
+        // by the driver to a supported size.  RTO_SMEM_CARVEOUT=<percent> overrides, 0 leaves the driver's choice.
+        {
+            const char* ce = getenv("RTO_SMEM_CARVEOUT");
+            int smem_per_sm = 0;
+            (void)cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+            int pct = -1;
+            if (ce) pct = atoi(ce) > 0 ? atoi(ce) : -1;
+            else if (smem_per_sm > 0) {
+                const size_t want = (size_t)tuned_blocks_per_sm(ds.occ_limit[v]) * (smem + 1024 + 64);
+                pct = (int)((want * 100 + (size_t)smem_per_sm - 1) / (size_t)smem_per_sm);
+            }
+            if (pct > 0 && pct <= 100 && cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess)
+                (void)cudaGetLastError();   // only a preference
+        }
     }
     const int n_supers = ((rw + kSuperX * kTileW - 1) / (kSuperX * kTileW)) * ((rh + kSuperY * kTileH - 1) / (kSuperY * kTileH));
     int grid = ds.num_sms * tuned_blocks_per_sm(ds.occ_limit[v]);

@@ -391,20 +391,13 @@ static cudaError_t launch_spp(const RenderArgs& a, int trace, cudaStream_t strea
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem)) != cudaSuccess) return e;
         ds.occ_limit[v] = occ > 0 ? occ : 1;
         ds.smem_set[v] = smem;
-        // Shared-memory carve-out.  The driver sizes it for the kernel's OCCUPANCY LIMIT (10 blocks), but the launch keeps fewer
-        // blocks resident (tuned_blocks_per_sm): ask for what those need — per block the dynamic scratch + the static word +
-        // the 1 KB the system reserves — so that the rest of the 256 KB stays L1 for the brick planes.  A hint, rounded up
-        // by the driver to a supported size.  RTO_SMEM_CARVEOUT=<percent> overrides, 0 leaves the driver's choice.
-        {
-            const char* ce = getenv("RTO_SMEM_CARVEOUT");
-            int smem_per_sm = 0;
-            (void)cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-            int pct = -1;
-            if (ce) pct = atoi(ce) > 0 ? atoi(ce) : -1;
-            else if (smem_per_sm > 0) {
-                const size_t want = (size_t)tuned_blocks_per_sm(ds.occ_limit[v]) * (smem + 1024 + 64);
-                pct = (int)((want * 100 + (size_t)smem_per_sm - 1) / (size_t)smem_per_sm);
-            }
+        // Shared-memory carve-out: left to the driver, which sizes it for the kernel's occupancy limit (10 blocks) although
+        // the launch keeps 8 resident.  Asking for just what the resident blocks need (more L1 for the brick planes) was
+        // measured (profiles/r02_ab_smem_carveout.json): render 0.1907 vs 0.1920 ms alone, but 5670 vs 6620 frames/s with four
+        // frames in flight — the GuidanceNet / filter CTAs of the neighbouring frames no longer find shared memory on the SM.
+        // RTO_SMEM_CARVEOUT=<percent> applies a preference for A/B runs.
+        if (const char* ce = getenv("RTO_SMEM_CARVEOUT")) {
+            const int pct = atoi(ce);
             if (pct > 0 && pct <= 100 && cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess)
                 (void)cudaGetLastError();   // only a preference
         }

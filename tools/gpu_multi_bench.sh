@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Round 2, second session, 2-GPU sanity: multi-GPU tests + the frame-sharded bench (rto_frame_sequence e2e, 4K tile split, CLI --num_gpus) at N = 2.
+# N-GPU check (tools/gpu_multi_bench.sh N K [notests]): multi-GPU tests + the frame-sharded bench (rto_frame_sequence e2e, 4K tile split, CLI --num_gpus) at N = 2.
 cd "$(dirname "$0")/.."
 N=${1:-2}; K=${2:-20}
 mkdir -p gpurun_out

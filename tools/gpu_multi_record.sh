@@ -2,7 +2,7 @@
 # Round 2, second session: N-GPU record of the final state — frame-sharded bench (incl. config 5 and the CLI) + CLI tile split, both read-back modes.
 cd "$(dirname "$0")/.."
 N=${1:-8}; K=${2:-20}
-bash tools/gpu_r2e.sh $N $K notests
+bash tools/gpu_multi_bench.sh $N $K notests
 C=/tmp/rto_cache/cli
 for mode in peer band; do
   extra=""; [ "$mode" = band ] && extra="--band_readback"
